@@ -1,0 +1,169 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference) in the build container.  Run from the repo root:
+
+    python tests/golden/make_golden.py
+
+Each .npz holds the inputs and the reference's outputs for one call on the
+CameraCalibration.correct() path.  Library versions are stored in
+versions.json.  The reference has no golden vectors of its own,
+so these files are what pins the oracle (tests/test_oracle_golden.py).
+"""
+import contextlib
+import io
+import json
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+import ref_shim  # noqa: E402
+
+ref_shim.install()
+warnings.simplefilter('ignore')
+
+import cv2  # noqa: E402
+import scipy  # noqa: E402
+from imgProcessor.camera.CameraCalibration import CameraCalibration  # noqa: E402
+from imgProcessor.camera.LensDistortion import LensDistortion  # noqa: E402
+from imgProcessor.filters.medianThreshold import medianThreshold  # noqa: E402
+
+from imgprocessor_b200 import synth  # noqa: E402
+
+
+def quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        r = fn(*a, **k)
+    return r, buf.getvalue()
+
+
+def make_lens(params, shape):
+    l = LensDistortion({})          # fresh dict: the default argument is shared (LensDistortion.py:26)
+    l.setCameraParams(*params)
+    l._coeffs['shape'] = shape
+    return l
+
+
+def save(name, **arrs):
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrs)
+    print('wrote', name, {k: (getattr(v, 'shape', None), getattr(v, 'dtype', None)) for k, v in arrs.items()})
+
+
+def main():
+    H, W = 96, 128
+    params = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(params), synth.dist_coeffs(params)
+
+    raw16 = synth.scene(H, W, 1, np.uint16)
+    raw32 = synth.scene(H, W, 2, np.float32)
+    dark = synth.dark_map(H, W)
+    flat = synth.flat_map(H, W, p_zero=2e-3)
+    flat[5, 7] = np.float32(1e-42)       # denormal flat -> huge quotient
+    flat[6, 9] = np.float32(-0.5)        # negative flat -> negative image values / medians
+
+    # ---- 1/2: full chain, keep_size True / False, u16 ---------------------
+    for keep in (True, False):
+        cal = CameraCalibration()
+        cal.addDarkCurrent(dark)
+        cal.addFlatField(flat)
+        cal.addLens(make_lens(params, (H, W)))
+        out, log = quiet(cal.correct, raw16, threshold=0.1, keep_size=keep)
+        save('correct_u16_keep%d' % keep, raw=raw16, dark=dark, flat=flat, K=K, dist=d,
+             out=np.ascontiguousarray(out), last_img=cal.last_img, bg=cal.temp['bg'],
+             log=np.array(log))
+
+    # ---- 3: f32 frame, threshold 0 (median skipped, no nan_to_num) --------
+    cal = CameraCalibration()
+    cal.addDarkCurrent(dark)
+    cal.addFlatField(flat)
+    cal.addLens(make_lens(params, (H, W)))
+    out, log = quiet(cal.correct, raw32, threshold=0)
+    save('correct_f32_thr0', raw=raw32, dark=dark, flat=flat, K=K, dist=d, out=out, log=np.array(log))
+
+    # ---- 4: only some calibrations present --------------------------------
+    cal = CameraCalibration()
+    cal.addFlatField(flat)
+    out, log = quiet(cal.correct, raw32, threshold=0.25)
+    save('correct_f32_flat_only', raw=raw32, flat=flat, out=out, log=np.array(log))
+
+    cal = CameraCalibration()
+    out, log = quiet(cal.correct, raw16, threshold=0.1)
+    save('correct_u16_nothing', raw=raw16, out=out, log=np.array(log))
+
+    # ---- 5: legacy tuple dark-current entry (offs + ascent*t, clipped) ----
+    cal = CameraCalibration()
+    offs = dark.astype(np.float64)
+    ascent = (synth.dark_map(H, W, seed=5).astype(np.float64) * 40.0)
+    ascent[3, 3] = 1e6                       # exercises the 2**depth-1 clip
+    cal.coeffs['dark current'].append((cal.currentTime() and __import__('time').localtime(), '', (offs.copy(), ascent.copy()), None))
+    cal.coeffs['shape'] = (H, W)
+    out, log = quiet(cal.correct, raw16, exposure_time=2.5, threshold=0.1)
+    save('correct_u16_legacy_dark', raw=raw16, offs=offs, ascent=ascent, exposure_time=np.float64(2.5),
+         out=out, bg=cal.temp['bg'], log=np.array(log))
+
+    # ---- 6: date selection -------------------------------------------------
+    cal = CameraCalibration()
+    d1 = dark
+    d2 = dark + np.float32(50)
+    d3 = dark + np.float32(200)
+    cal.addDarkCurrent(d1, date='01 Jan 15 - 10:00')
+    cal.addDarkCurrent(d3, date='01 Jan 17 - 10:00')
+    cal.addDarkCurrent(d2, date='01 Jan 16 - 10:00')
+    outs = {}
+    for tag, date in (('none', None), ('mid', '01 Jun 16 - 00:00'), ('old', '01 Jan 14 - 00:00'),
+                      ('new', '01 Jan 18 - 00:00'), ('bad', 'not a date')):
+        o, _ = quiet(cal.correct, raw16, threshold=0, date=date)
+        outs['out_' + tag] = o
+    save('correct_u16_dates', raw=raw16, d1=d1, d2=d2, d3=d3, **outs)
+
+    # ---- 7: medianThreshold direct ----------------------------------------
+    for tag, img in (('u16', raw16), ('f32', raw32)):
+        for size in (3, 5):
+            for cond in ('>', '<'):
+                o, ind = medianThreshold(img, threshold=0.1, size=size, condition=cond, copy=True)
+                save('median_%s_s%d_%s' % (tag, size, 'gt' if cond == '>' else 'lt'),
+                     img=img, out=o, ind=ind)
+    # zeros / negative medians / blur == 0 cases
+    z = raw32.copy()
+    z[10:40, 10:60] = 0
+    z[20, 20] = 5
+    z[50:60, 50:60] *= -1
+    o, ind = medianThreshold(z, threshold=0.3, size=3)
+    save('median_f32_zeros', img=z, out=o, ind=ind, threshold=np.float64(0.3))
+
+    # ---- 8: LensDistortion.correct direct, every dtype the callers use ----
+    Hr, Wr = 125, 166                          # realistic coefficients scaled to a quarter-size frame
+    pr = list(synth.lens_realistic())
+    pr[0] /= 4; pr[1] /= 4; pr[2] /= 4; pr[3] /= 4
+    for tag, dt in (('u8', np.uint8), ('u16', np.uint16), ('f32', np.float32), ('f64', np.float64)):
+        img = synth.scene(Hr, Wr, 3, dt) if dt != np.float64 else synth.scene(Hr, Wr, 3, np.float32).astype(np.float64) * 1.000000123
+        for keep in (False, True):
+            l = make_lens(pr, (Hr, Wr))
+            o = l.correct(img, keepSize=keep, borderValue=7 if keep else 0)
+            extra = dict(mapx=l.mapx, mapy=l.mapy) if (tag == 'f32' and keep) else {}
+            save('lens_%s_keep%d' % (tag, keep), img=img, out=np.ascontiguousarray(o), roi=np.array(l.roi),
+                 K=l.coeffs['cameraMatrix'], dist=l.coeffs['distortionCoeffs'],
+                 border=np.float64(7 if keep else 0), **extra)
+
+    # ---- 9: maps + P + roi for three lenses --------------------------------
+    for tag, (hh, ww, pp) in (('moderate', (96, 128, synth.lens_moderate(96, 128))),
+                              ('strong', (128, 128, synth.lens_strong(128, 128))),
+                              ('realistic', (Hr, Wr, pr))):
+        l = make_lens(pp, (hh, ww))
+        mx, my = l.getUndistortRectifyMap(ww, hh)
+        P, roi = cv2.getOptimalNewCameraMatrix(l.coeffs['cameraMatrix'], l.coeffs['distortionCoeffs'],
+                                               (ww, hh), 1, (ww, hh))
+        save('maps_' + tag, K=l.coeffs['cameraMatrix'], dist=l.coeffs['distortionCoeffs'], P=P,
+             roi=np.array(roi), mapx=mx, mapy=my, shape=np.array([hh, ww]))
+
+    with open(os.path.join(HERE, 'versions.json'), 'w') as f:
+        json.dump({'numpy': np.__version__, 'scipy': scipy.__version__, 'cv2': cv2.__version__,
+                   'reference': 'radjkarl/imgProcessor 0.2.5 (/root/reference), unmodified, under ref_shim'}, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()

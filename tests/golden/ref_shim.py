@@ -1,0 +1,39 @@
+"""Import shim that lets the UNMODIFIED reference (/root/reference, imgProcessor
+0.2.5) import under numpy 2.x without its absent `fancytools` dependency.
+Used only by make_golden.py in the build container; the reference does not
+exist on the GPU box.  Nothing here patches reference code: it re-adds two numpy
+aliases the reference uses (np.float, np.asfarray; CameraCalibration.py:408,410,
+medianThreshold.py:18) and registers empty stand-ins for import-time-only modules
+(SingleTimeEffectDetection.py:10, imgSignal.py:8, DarkCurrentMap.py)."""
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOT = '/root/reference'
+
+
+def install():
+    if not hasattr(np, 'float'):
+        np.float = float
+    if not hasattr(np, 'asfarray'):
+        def asfarray(a, dtype=np.float64):
+            dt = np.dtype(dtype)
+            if not np.issubdtype(dt, np.inexact):
+                dt = np.dtype(np.float64)
+            return np.asarray(a, dtype=dt)
+        np.asfarray = asfarray
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+
+    for pkg in ('fancytools', 'fancytools.math', 'fancytools.os', 'fancytools.fit'):
+        mod(pkg)
+    mod('fancytools.math.MaskedMovingAverage', MaskedMovingAverage=None)
+    mod('fancytools.math.findXAt', findXAt=None)
+    mod('fancytools.os.PathStr', PathStr=str)
+    mod('fancytools.math.linRegressUsingMasked2dArrays', linRegressUsingMasked2dArrays=None)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
