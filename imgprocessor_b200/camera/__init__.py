@@ -1,0 +1,2 @@
+from .CameraCalibration import CameraCalibration  # noqa: F401
+from .LensDistortion import LensDistortion  # noqa: F401

@@ -1,0 +1,434 @@
+// imgcorr_api.cu — the C ABI declared in include/imgcorr.h: context, calibration upload,
+// kernel entry points, the device-resident chain and the host-buffer streaming pipeline.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/imgcorr.h"
+#include "imgcorr_kernels.cuh"
+
+using namespace imgcorr;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(IMGCORR_ERR_CUDA, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+#define CK(call)                                             \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+struct HostSlot {
+    void* d_raw = nullptr;
+    void* d_out = nullptr;
+    void* h_raw = nullptr;
+    void* h_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_k = nullptr, ev_out = nullptr;
+};
+
+struct imgcorr_ctx {
+    int device = 0, H = 0, W = 0, sm_count = 148;
+    float* dark = nullptr;
+    float* ascent = nullptr;
+    float* flat = nullptr;
+    double exposure = 0.0, maxval = 65535.0;
+    bool has_lens = false;
+    LensConst lens{};
+    int k1_variant = 0, k2_variant = 0, host_slots = 4;
+    long long launches = 0;
+    float* mid[2] = {nullptr, nullptr};
+    // host pipeline
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    std::vector<HostSlot> slots;
+    size_t slot_raw_bytes = 0, slot_out_bytes = 0;
+};
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(ctx)                                                           \
+    if (!(ctx)) return fail(IMGCORR_ERR_INVALID, "null context");            \
+    DeviceGuard guard__((ctx)->device);                                      \
+    if (!guard__.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice")
+
+extern "C" IMGCORR_API const char* imgcorr_last_error(void) { return g_err.c_str(); }
+extern "C" IMGCORR_API int imgcorr_version(void) { return IMGCORR_VERSION; }
+
+extern "C" IMGCORR_API int imgcorr_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    return n;
+}
+
+extern "C" IMGCORR_API int imgcorr_ctx_create(int device, int height, int width, imgcorr_ctx** out_ctx) {
+    if (!out_ctx) return fail(IMGCORR_ERR_INVALID, "out_ctx is null");
+    *out_ctx = nullptr;
+    if (height <= 0 || width <= 0) return fail(IMGCORR_ERR_INVALID, "bad frame shape %d x %d", height, width);
+    int n = 0;
+    CK(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(IMGCORR_ERR_INVALID, "device %d out of range (%d devices)", device, n);
+    DeviceGuard g(device);
+    if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(IMGCORR_ERR_CUDA, "device %d is sm_%d%d; libimgcorr is built for sm_100a only", device, prop.major,
+                    prop.minor);
+    imgcorr_ctx* c = new (std::nothrow) imgcorr_ctx();
+    if (!c) return fail(IMGCORR_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    c->H = height;
+    c->W = width;
+    c->sm_count = prop.multiProcessorCount;
+    *out_ctx = c;
+    return IMGCORR_OK;
+}
+
+static void free_slots(imgcorr_ctx* c) {
+    for (auto& s : c->slots) {
+        if (s.d_raw) cudaFree(s.d_raw);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_raw) cudaFreeHost(s.h_raw);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.ev_in) cudaEventDestroy(s.ev_in);
+        if (s.ev_k) cudaEventDestroy(s.ev_k);
+        if (s.ev_out) cudaEventDestroy(s.ev_out);
+    }
+    c->slots.clear();
+    c->slot_raw_bytes = c->slot_out_bytes = 0;
+}
+
+extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
+    if (!c) return IMGCORR_OK;
+    DeviceGuard g(c->device);
+    cudaDeviceSynchronize();
+    free_slots(c);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_k) cudaStreamDestroy(c->s_k);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    cudaFree(c->dark);
+    cudaFree(c->ascent);
+    cudaFree(c->flat);
+    cudaFree(c->mid[0]);
+    cudaFree(c->mid[1]);
+    delete c;
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value) {
+    if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
+    switch (key) {
+        case IMGCORR_OPT_K1_VARIANT:
+            if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
+            c->k1_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_K2_VARIANT:
+            c->k2_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_HOST_SLOTS:
+            if (value < 2 || value > 64) return fail(IMGCORR_ERR_INVALID, "host slots %d not in [2,64]", value);
+            if (value != c->host_slots) {
+                DeviceGuard g(c->device);
+                cudaDeviceSynchronize();
+                free_slots(c);
+                c->host_slots = value;
+            }
+            return IMGCORR_OK;
+    }
+    return fail(IMGCORR_ERR_INVALID, "unknown option %d", key);
+}
+
+extern "C" IMGCORR_API long long imgcorr_launch_count(const imgcorr_ctx* c) { return c ? c->launches : 0; }
+
+static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_device) {
+    const size_t bytes = (size_t)c->H * c->W * sizeof(float);
+    if (!src) {
+        if (*slot) { CK(cudaDeviceSynchronize()); CK(cudaFree(*slot)); *slot = nullptr; }
+        return IMGCORR_OK;
+    }
+    if (!*slot) CK(cudaMalloc((void**)slot, bytes));
+    CK(cudaMemcpy(*slot, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* c, const float* dark, const float* ascent, double exposure_time,
+                                int depth_bits, int on_device) {
+    GUARD(c);
+    if (!dark && ascent) return fail(IMGCORR_ERR_INVALID, "ascent given without offset map");
+    if (ascent && (depth_bits < 1 || depth_bits > 62)) return fail(IMGCORR_ERR_INVALID, "depth_bits %d", depth_bits);
+    if (ascent && !(exposure_time == exposure_time)) return fail(IMGCORR_ERR_INVALID, "exposure_time is NaN");
+    int r = upload_map(c, &c->dark, dark, on_device);
+    if (r) return r;
+    r = upload_map(c, &c->ascent, ascent, on_device);
+    if (r) return r;
+    c->exposure = exposure_time;
+    c->maxval = ascent ? ldexp(1.0, depth_bits) - 1.0 : 65535.0;
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_set_flat(imgcorr_ctx* c, const float* flat, int on_device) {
+    GUARD(c);
+    return upload_map(c, &c->flat, flat, on_device);
+}
+
+extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], const double dist[5], const double P[9]) {
+    if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
+    if (!K) { c->has_lens = false; return IMGCORR_OK; }
+    if (!dist || !P) return fail(IMGCORR_ERR_INVALID, "dist / P is null");
+    LensConst L{};
+    if (!invert3x3(P, L.ir)) return fail(IMGCORR_ERR_INVALID, "new camera matrix P is singular");
+    L.k1 = dist[0]; L.k2 = dist[1]; L.p1 = dist[2]; L.p2 = dist[3]; L.k3 = dist[4];
+    L.fx = K[0]; L.fy = K[4]; L.cx = K[2]; L.cy = K[5];
+    L.affine = (L.ir[6] == 0.0 && L.ir[7] == 0.0 && L.ir[8] == 1.0) ? 1 : 0;
+    c->lens = L;
+    c->has_lens = true;
+    return IMGCORR_OK;
+}
+
+static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, void* out, uint8_t* mask, int n, double thr, int ksize,
+                   int cond, int flags) {
+    if (!raw || !out) return fail(IMGCORR_ERR_INVALID, "null image pointer");
+    if (n < 0) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n);
+    if (!(thr > 0.0)) ksize = 0;                      // also NaN
+    if (ksize != 0 && ksize != 3 && ksize != 5) return fail(IMGCORR_ERR_INVALID, "ksize %d (0, 3 or 5)", ksize);
+    if (cond != IMGCORR_COND_GT && cond != IMGCORR_COND_LT) return fail(IMGCORR_ERR_INVALID, "cond %d", cond);
+    a = K1Args{};
+    a.raw = raw; a.out = out; a.mask = ksize ? mask : nullptr;
+    a.H = c->H; a.W = c->W; a.n_frames = n; a.ksize = ksize;
+    int f = 0;
+    if ((flags & IMGCORR_DO_DARK) && c->dark) {
+        f |= FLAG_DARK; a.dark = c->dark;
+        if (c->ascent) { f |= FLAG_DARK_LINEAR; a.ascent = c->ascent; }
+    }
+    if ((flags & IMGCORR_DO_FLAT) && c->flat) { f |= FLAG_FLAT; a.flat = c->flat; }
+    if (flags & IMGCORR_DO_NAN_TO_NUM) f |= FLAG_NAN_TO_NUM;
+    a.pw.flags = f; a.pw.exposure_time = c->exposure; a.pw.max_value = c->maxval;
+    a.pred = make_predicate(thr, cond == IMGCORR_COND_LT ? COND_LT : COND_GT);
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_pointwise_median(imgcorr_ctx* c, const void* raw_dev, int raw_dtype, void* out_dev, int out_dtype,
+                                        uint8_t* mask_dev, int n_frames, double threshold, int ksize, int cond,
+                                        int flags, void* stream) {
+    GUARD(c);
+    K1Args a;
+    int r = fill_k1(c, a, raw_dev, out_dev, mask_dev, n_frames, threshold, ksize, cond, flags);
+    if (r) return r;
+    int l = 0;
+    cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e == cudaErrorInvalidValue && l == 0)
+        return fail(IMGCORR_ERR_INVALID, "unsupported dtype pair raw=%d out=%d", raw_dtype, out_dtype);
+    if (e == cudaErrorNotSupported) return fail(IMGCORR_ERR_INVALID, "TMA variant requested but shape/alignment not eligible");
+    if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
+    return IMGCORR_OK;
+}
+
+static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, int n, const float* mapx,
+                  const float* mapy, double border, int x0, int y0, int ow, int oh, cudaStream_t st) {
+    if (!src || !dst) return fail(IMGCORR_ERR_INVALID, "null image pointer");
+    if (n < 0) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n);
+    if (!mapx && !c->has_lens) return fail(IMGCORR_ERR_STATE, "no lens set");
+    if (x0 < 0 || y0 < 0 || ow < 0 || oh < 0 || x0 + ow > c->W || y0 + oh > c->H)
+        return fail(IMGCORR_ERR_INVALID, "output window (%d,%d,%d,%d) outside %dx%d frame", x0, y0, ow, oh, c->W, c->H);
+    K2Args a{};
+    a.src = src; a.dst = dst; a.mapx = mapx; a.mapy = mapy;
+    a.H = c->H; a.W = c->W; a.n_frames = n;
+    a.x0 = x0; a.y0 = y0; a.ow = ow; a.oh = oh;
+    a.border = border_for_dtype(sdt == DT_U8, sdt == DT_U16, border);
+    a.lens = c->lens;
+    int l = 0;
+    cudaError_t e = launch_k2(a, sdt, ddt, c->k2_variant, st, &l);
+    c->launches += l;
+    if (e == cudaErrorInvalidValue && l == 0)
+        return fail(IMGCORR_ERR_INVALID, "unsupported dtype pair src=%d dst=%d", sdt, ddt);
+    if (e != cudaSuccess) return cuda_fail(e, "K2 launch");
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_undistort(imgcorr_ctx* c, const void* src_dev, int src_dtype, void* dst_dev, int dst_dtype,
+                                 int n_frames, double border_value, int x0, int y0, int ow, int oh, void* stream) {
+    GUARD(c);
+    return run_k2(c, src_dev, src_dtype, dst_dev, dst_dtype, n_frames, nullptr, nullptr, border_value, x0, y0, ow, oh,
+                  (cudaStream_t)stream);
+}
+
+extern "C" IMGCORR_API int imgcorr_remap(imgcorr_ctx* c, const void* src_dev, int src_dtype, void* dst_dev, int dst_dtype,
+                             int n_frames, const float* mapx_dev, const float* mapy_dev, double border_value,
+                             void* stream) {
+    GUARD(c);
+    if (!mapx_dev || !mapy_dev) return fail(IMGCORR_ERR_INVALID, "null map pointer");
+    return run_k2(c, src_dev, src_dtype, dst_dev, dst_dtype, n_frames, mapx_dev, mapy_dev, border_value, 0, 0, c->W,
+                  c->H, (cudaStream_t)stream);
+}
+
+extern "C" IMGCORR_API int imgcorr_undistort_maps(imgcorr_ctx* c, float* mapx_dev, float* mapy_dev, void* stream) {
+    GUARD(c);
+    if (!c->has_lens) return fail(IMGCORR_ERR_STATE, "no lens set");
+    if (!mapx_dev || !mapy_dev) return fail(IMGCORR_ERR_INVALID, "null map pointer");
+    int l = 0;
+    cudaError_t e = launch_write_maps(c->lens, mapx_dev, mapy_dev, c->H, c->W, (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "map kernel launch");
+    return IMGCORR_OK;
+}
+
+// one frame (or a group of frames) through K1 -> K2 on `st`
+static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* out, int out_dtype, int n, double thr,
+                        int ksize, int flags, bool lens, double border, int x0, int y0, int ow, int oh, cudaStream_t st) {
+    if (out_dtype != DT_F32 && out_dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "out_dtype must be F32 or F64");
+    if (raw_dtype == DT_F64) return fail(IMGCORR_ERR_INVALID, "float64 frames: convert to float32 first (the chain computes in float32)");
+    const size_t npx = (size_t)c->H * c->W;
+    const size_t raw_stride = npx * dtype_size(raw_dtype);
+    if (!lens) {
+        if (x0 != 0 || y0 != 0 || ow != c->W || oh != c->H)
+            return fail(IMGCORR_ERR_INVALID, "output window without a lens");
+        K1Args a;
+        int r = fill_k1(c, a, raw, out, nullptr, n, thr, ksize, IMGCORR_COND_GT, flags);
+        if (r) return r;
+        int l = 0;
+        cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, st, &l);
+        c->launches += l;
+        if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
+        return IMGCORR_OK;
+    }
+    for (int i = 0; i < 2; ++i)
+        if (!c->mid[i]) CK(cudaMalloc((void**)&c->mid[i], npx * sizeof(float)));
+    const size_t out_stride = (size_t)ow * oh * dtype_size(out_dtype);
+    for (int f = 0; f < n; ++f) {
+        float* mid = c->mid[f & 1];
+        K1Args a;
+        int r = fill_k1(c, a, (const char*)raw + f * raw_stride, mid, nullptr, 1, thr, ksize, IMGCORR_COND_GT, flags);
+        if (r) return r;
+        int l = 0;
+        cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, st, &l);
+        c->launches += l;
+        if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
+        r = run_k2(c, mid, DT_F32, (char*)out + f * out_stride, out_dtype, 1, nullptr, nullptr, border, x0, y0, ow, oh, st);
+        if (r) return r;
+    }
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_correct_batch(imgcorr_ctx* c, const void* raw_dev, int raw_dtype, void* out_dev, int out_dtype,
+                                     int n_frames, double threshold, int ksize, int flags, int use_lens,
+                                     double border_value, int x0, int y0, int ow, int oh, void* stream) {
+    GUARD(c);
+    if (!raw_dev || !out_dev) return fail(IMGCORR_ERR_INVALID, "null image pointer");
+    const bool lens = use_lens && c->has_lens;
+    if (!lens) { x0 = 0; y0 = 0; ow = c->W; oh = c->H; }
+    return chain_frames(c, raw_dev, raw_dtype, out_dev, out_dtype, n_frames, threshold, ksize, flags, lens, border_value,
+                        x0, y0, ow, oh, (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int ensure_pipeline(imgcorr_ctx* c, size_t raw_bytes, size_t out_bytes) {
+    if (!c->s_in) {
+        CK(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    }
+    if ((int)c->slots.size() == c->host_slots && c->slot_raw_bytes >= raw_bytes && c->slot_out_bytes >= out_bytes)
+        return IMGCORR_OK;
+    CK(cudaDeviceSynchronize());
+    free_slots(c);
+    c->slots.resize(c->host_slots);
+    for (auto& s : c->slots) {
+        CK(cudaMalloc(&s.d_raw, raw_bytes));
+        CK(cudaMalloc(&s.d_out, out_bytes));
+        CK(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_k, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
+    }
+    c->slot_raw_bytes = raw_bytes;
+    c->slot_out_bytes = out_bytes;
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_host, int raw_dtype, void* out_host, int out_dtype,
+                                    int n_frames, double threshold, int ksize, int flags, int use_lens,
+                                    double border_value, int x0, int y0, int ow, int oh) {
+    GUARD(c);
+    if (!raw_host || !out_host) return fail(IMGCORR_ERR_INVALID, "null image pointer");
+    if (n_frames < 0) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n_frames);
+    if (raw_dtype < DT_U8 || raw_dtype > DT_F32) return fail(IMGCORR_ERR_INVALID, "raw_dtype %d (U8, U16 or F32)", raw_dtype);
+    if (out_dtype != DT_F32 && out_dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "out_dtype must be F32 or F64");
+    const bool lens = use_lens && c->has_lens;
+    if (!lens) { x0 = 0; y0 = 0; ow = c->W; oh = c->H; }
+    const size_t raw_bytes = (size_t)c->H * c->W * dtype_size(raw_dtype);
+    const size_t out_bytes = (size_t)ow * oh * dtype_size(out_dtype);
+    int r = ensure_pipeline(c, raw_bytes, out_bytes);
+    if (r) return r;
+    const bool in_pinned = is_pinned(raw_host), out_pinned = is_pinned(out_host);
+    for (auto& s : c->slots) {
+        if (!in_pinned && !s.h_raw) CK(cudaHostAlloc(&s.h_raw, c->slot_raw_bytes, cudaHostAllocDefault));
+        if (!out_pinned && !s.h_out) CK(cudaHostAlloc(&s.h_out, c->slot_out_bytes, cudaHostAllocDefault));
+    }
+    const int ns = (int)c->slots.size();
+    auto retire = [&](int frame) -> int {      // frame's D2H has been enqueued on s_out in slot frame % ns
+        HostSlot& s = c->slots[frame % ns];
+        CK(cudaEventSynchronize(s.ev_out));
+        if (!out_pinned) memcpy((char*)out_host + (size_t)frame * out_bytes, s.h_out, out_bytes);
+        return IMGCORR_OK;
+    };
+    for (int f = 0; f < n_frames; ++f) {
+        HostSlot& s = c->slots[f % ns];
+        if (f >= ns) { r = retire(f - ns); if (r) return r; }
+        const char* src = (const char*)raw_host + (size_t)f * raw_bytes;
+        if (!in_pinned) { memcpy(s.h_raw, src, raw_bytes); src = (const char*)s.h_raw; }
+        CK(cudaMemcpyAsync(s.d_raw, src, raw_bytes, cudaMemcpyHostToDevice, c->s_in));
+        CK(cudaEventRecord(s.ev_in, c->s_in));
+        CK(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
+        r = chain_frames(c, s.d_raw, raw_dtype, s.d_out, out_dtype, 1, threshold, ksize, flags, lens, border_value, x0, y0,
+                         ow, oh, c->s_k);
+        if (r) return r;
+        CK(cudaEventRecord(s.ev_k, c->s_k));
+        CK(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
+        void* dst = out_pinned ? (void*)((char*)out_host + (size_t)f * out_bytes) : s.h_out;
+        CK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDeviceToHost, c->s_out));
+        CK(cudaEventRecord(s.ev_out, c->s_out));
+    }
+    for (int f = (n_frames > ns ? n_frames - ns : 0); f < n_frames; ++f) { r = retire(f); if (r) return r; }
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr) {
+    if (!out_ptr) return fail(IMGCORR_ERR_INVALID, "out_ptr is null");
+    *out_ptr = nullptr;
+    CK(cudaHostAlloc(out_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_host_free(void* ptr) {
+    if (!ptr) return IMGCORR_OK;
+    CK(cudaFreeHost(ptr));
+    return IMGCORR_OK;
+}

@@ -1,0 +1,50 @@
+// imgcorr_kernels.cuh — launch-side declarations shared by the kernel translation units
+// and the C-ABI layer (imgcorr_api.cu).  Not part of the public interface (include/imgcorr.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "imgcorr_core.cuh"
+
+namespace imgcorr {
+
+enum DType : int { DT_U8 = 0, DT_U16 = 1, DT_F32 = 2, DT_F64 = 3 };
+
+inline size_t dtype_size(int dt) { return dt == DT_U8 ? 1 : dt == DT_U16 ? 2 : dt == DT_F32 ? 4 : 8; }
+
+// K1: fused dark / flat / nan_to_num / NxN median-threshold --------------------------------
+struct K1Args {
+    const void* raw;        // [n_frames][H][W] of raw dtype
+    const float* dark;      // [H][W] or null   (offset map when FLAG_DARK_LINEAR)
+    const float* ascent;    // [H][W] or null   (FLAG_DARK_LINEAR only)
+    const float* flat;      // [H][W] or null
+    void* out;              // [n_frames][H][W] of out dtype
+    uint8_t* mask;          // [n_frames][H][W] or null
+    int H, W, n_frames;
+    int ksize;              // 0 (pointwise only), 3, 5
+    PointwiseConst pw;
+    PredicateConst pred;
+};
+
+// variant: 0 = pick automatically, 1 = generic (plain coalesced loads), 2 = TMA-staged
+cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count,
+                      cudaStream_t stream, int* launches);
+bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype);
+
+// K2: undistortion remap ---------------------------------------------------------------------
+struct K2Args {
+    const void* src;        // [n_frames][H][W]
+    void* dst;              // [n_frames][oh][ow]
+    const float* mapx;      // explicit maps [H][W] (full frame) or null -> analytic Brown-Conrady
+    const float* mapy;
+    int H, W, n_frames;
+    int x0, y0, ow, oh;     // output window in full-frame coordinates (keep_size=False crop)
+    double border;
+    LensConst lens;
+};
+
+cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t stream,
+                      int* launches);
+cudaError_t launch_write_maps(const LensConst& lens, float* mapx, float* mapy, int H, int W,
+                              cudaStream_t stream, int* launches);
+
+}  // namespace imgcorr

@@ -1,0 +1,144 @@
+// K2 — lens undistortion: per output pixel evaluate the Brown-Conrady model analytically
+// (float64, one rounding to float32 — no map arrays are read), convert to OpenCV's 5-bit
+// fixed-point coordinates and gather the bilinear blend from the K1 output through L1/L2.
+//
+// Replaces  LensDistortion.correct()  camera/LensDistortion.py:316-330:
+//   cv2.getOptimalNewCameraMatrix (host, stays cv2)  ->  P           :350-353
+//   cv2.initUndistortRectifyMap(K, d, None, P, CV_32FC1)              :355-357   (device, analytic)
+//   cv2.remap(INTER_LINEAR, BORDER_CONSTANT, borderValue)             :323-326   (device)
+//   optional crop to roi                                              :327-329   (output window)
+// The same kernel also serves explicit float32 maps (distortImage, parity tests against
+// cv2's own maps).  When n_frames > 1 the coordinates and weights of a pixel are computed once
+// and applied to every frame of the launch.
+#include "imgcorr_kernels.cuh"
+
+namespace imgcorr {
+
+constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = 4;     // CTA = 32 x 8 threads, tile = 32 x 32 outputs
+
+template <typename SrcT> __device__ __forceinline__ SrcT border_cast(double b) { return (SrcT)b; }
+
+template <typename SrcT, typename DstT> struct Blend;
+template <> struct Blend<float, float> {
+    static __device__ __forceinline__ float run(float a, float b, float c, float d, const FixedCoord& fc) {
+        float w00, w01, w10, w11; bilinear_weights(fc.fx, fc.fy, w00, w01, w10, w11);
+        return blend_f32(a, b, c, d, w00, w01, w10, w11);
+    }
+};
+template <> struct Blend<float, double> {
+    static __device__ __forceinline__ double run(float a, float b, float c, float d, const FixedCoord& fc) {
+        return (double)Blend<float, float>::run(a, b, c, d, fc);
+    }
+};
+template <> struct Blend<double, double> {
+    static __device__ __forceinline__ double run(double a, double b, double c, double d, const FixedCoord& fc) {
+        float w00, w01, w10, w11; bilinear_weights(fc.fx, fc.fy, w00, w01, w10, w11);
+        return blend_f64(a, b, c, d, w00, w01, w10, w11);
+    }
+};
+template <> struct Blend<uint16_t, uint16_t> {
+    static __device__ __forceinline__ uint16_t run(uint16_t a, uint16_t b, uint16_t c, uint16_t d, const FixedCoord& fc) {
+        return sat_u16(Blend<float, float>::run((float)a, (float)b, (float)c, (float)d, fc));
+    }
+};
+template <> struct Blend<uint8_t, uint8_t> {
+    static __device__ __forceinline__ uint8_t run(uint8_t a, uint8_t b, uint8_t c, uint8_t d, const FixedCoord& fc) {
+        return (uint8_t)blend_u8(a, b, c, d, fc.fx, fc.fy);
+    }
+};
+
+template <typename SrcT, typename DstT>
+__device__ __forceinline__ DstT remap_pixel(const SrcT* __restrict__ src, int H, int W, const FixedCoord& c, SrcT bval) {
+    const int ix = c.ix, iy = c.iy;
+    SrcT v00, v01, v10, v11;
+    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
+        const SrcT* p = src + (size_t)iy * W + ix;
+        v00 = __ldg(p); v01 = __ldg(p + 1); v10 = __ldg(p + W); v11 = __ldg(p + W + 1);
+    } else {
+        // OpenCV: a window entirely outside the image is the border value itself, not a blend of it
+        if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return (DstT)bval;
+        const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+        const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+        const SrcT* p = src + (ptrdiff_t)iy * W + ix;
+        v00 = (x0 && y0) ? __ldg(p) : bval;
+        v01 = (x1 && y0) ? __ldg(p + 1) : bval;
+        v10 = (x0 && y1) ? __ldg(p + W) : bval;
+        v11 = (x1 && y1) ? __ldg(p + W + 1) : bval;
+    }
+    return Blend<SrcT, DstT>::run(v00, v01, v10, v11, c);
+}
+
+template <typename SrcT, typename DstT, bool ANALYTIC>
+__global__ void __launch_bounds__(K2_BX * K2_BY) k2_remap_kernel(K2Args a) {
+    const int ox = blockIdx.x * K2_BX + (threadIdx.x % K2_BX);
+    const int ty = threadIdx.x / K2_BX;
+    if (ox >= a.ow) return;
+    const int u = ox + a.x0;
+    const SrcT bval = border_cast<SrcT>(a.border);
+    const size_t src_stride = (size_t)a.H * a.W, dst_stride = (size_t)a.oh * a.ow;
+#pragma unroll
+    for (int j = 0; j < K2_ROWS; ++j) {
+        const int oy = blockIdx.y * (K2_BY * K2_ROWS) + ty + j * K2_BY;
+        if (oy >= a.oh) break;
+        const int v = oy + a.y0;
+        float mx, my;
+        if (ANALYTIC) {
+            undistort_map(a.lens, u, v, mx, my);
+        } else {
+            mx = __ldg(a.mapx + (size_t)v * a.W + u);
+            my = __ldg(a.mapy + (size_t)v * a.W + u);
+        }
+        const FixedCoord c = fixed_coord(mx, my);
+        const SrcT* src = (const SrcT*)a.src;
+        DstT* dst = (DstT*)a.dst + (size_t)oy * a.ow + ox;
+        for (int f = 0; f < a.n_frames; ++f) {
+            *dst = remap_pixel<SrcT, DstT>(src, a.H, a.W, c, bval);
+            src += src_stride;
+            dst += dst_stride;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k2_write_maps_kernel(LensConst lens, float* mapx, float* mapy, int H, int W) {
+    const int u = blockIdx.x * 32 + (threadIdx.x % 32);
+    const int v = blockIdx.y * 8 + (threadIdx.x / 32);
+    if (u >= W || v >= H) return;
+    float mx, my;
+    undistort_map(lens, u, v, mx, my);
+    mapx[(size_t)v * W + u] = mx;
+    mapy[(size_t)v * W + u] = my;
+}
+
+template <typename SrcT, typename DstT>
+static cudaError_t launch_t(const K2Args& a, cudaStream_t st) {
+    dim3 grid((a.ow + K2_BX - 1) / K2_BX, (a.oh + K2_BY * K2_ROWS - 1) / (K2_BY * K2_ROWS));
+    if (a.mapx) k2_remap_kernel<SrcT, DstT, false><<<grid, K2_BX * K2_BY, 0, st>>>(a);
+    else k2_remap_kernel<SrcT, DstT, true><<<grid, K2_BX * K2_BY, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t st, int* launches) {
+    (void)variant;
+    if (a.n_frames <= 0 || a.ow <= 0 || a.oh <= 0) return cudaSuccess;
+    if (a.x0 < 0 || a.y0 < 0 || a.x0 + a.ow > a.W || a.y0 + a.oh > a.H) return cudaErrorInvalidValue;
+    if ((a.mapx == nullptr) != (a.mapy == nullptr)) return cudaErrorInvalidValue;
+    if (launches) ++*launches;
+    if (src_dtype == DT_F32 && dst_dtype == DT_F32) return launch_t<float, float>(a, st);
+    if (src_dtype == DT_F32 && dst_dtype == DT_F64) return launch_t<float, double>(a, st);
+    if (src_dtype == DT_F64 && dst_dtype == DT_F64) return launch_t<double, double>(a, st);
+    if (src_dtype == DT_U16 && dst_dtype == DT_U16) return launch_t<uint16_t, uint16_t>(a, st);
+    if (src_dtype == DT_U8 && dst_dtype == DT_U8) return launch_t<uint8_t, uint8_t>(a, st);
+    if (launches) --*launches;
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_write_maps(const LensConst& lens, float* mapx, float* mapy, int H, int W, cudaStream_t st,
+                              int* launches) {
+    if (H <= 0 || W <= 0) return cudaSuccess;
+    dim3 grid((W + 31) / 32, (H + 7) / 8);
+    k2_write_maps_kernel<<<grid, 256, 0, st>>>(lens, mapx, mapy, H, W);
+    if (launches) ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace imgcorr

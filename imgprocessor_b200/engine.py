@@ -1,0 +1,292 @@
+"""Engine: one libimgcorr context (device, frame shape) with torch tensors as the device buffers.
+
+torch is plumbing only: it owns device memory and streams; every kernel that runs is one of the
+hand-written sm_100a kernels in csrc/, reached through the C ABI of include/imgcorr.h.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import DO_DARK, DO_FLAT, DO_NAN_TO_NUM  # noqa: F401  (re-exported)
+
+_TORCH = None
+
+
+def torch():
+    global _TORCH
+    if _TORCH is None:
+        import torch as _t
+        _TORCH = _t
+    return _TORCH
+
+
+def _dtype_code(t):
+    tt = torch()
+    table = {tt.uint8: _lib.U8, tt.uint16: _lib.U16, tt.float32: _lib.F32, tt.float64: _lib.F64}
+    if t not in table:
+        raise TypeError('unsupported frame dtype %s (uint8, uint16, float32, float64)' % (t,))
+    return table[t]
+
+
+def _torch_dtype(code):
+    tt = torch()
+    return {_lib.U8: tt.uint8, _lib.U16: tt.uint16, _lib.F32: tt.float32, _lib.F64: tt.float64}[code]
+
+
+NP_CODES = {np.dtype(np.uint8): _lib.U8, np.dtype(np.uint16): _lib.U16, np.dtype(np.float32): _lib.F32,
+            np.dtype(np.float64): _lib.F64}
+
+
+def require_cuda():
+    tt = torch()
+    if not tt.cuda.is_available():
+        raise RuntimeError('imgprocessor_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    return tt
+
+
+class Engine(object):
+    def __init__(self, height, width, device=None):
+        tt = require_cuda()
+        self.lib = _lib.lib()
+        if device is None:
+            device = tt.cuda.current_device()
+        self.device_index = tt.device('cuda', device).index if not isinstance(device, int) else device
+        self.device = tt.device('cuda', self.device_index)
+        self.H, self.W = int(height), int(width)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.imgcorr_ctx_create(self.device_index, self.H, self.W, ctypes.byref(h)))
+        self._h = h
+        self.has_dark = self.has_flat = self.has_lens = False
+        self._tokens = {}
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_h', None):
+            self.lib.imgcorr_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key, value):
+        _lib.check(self.lib.imgcorr_set_option(self._h, key, value))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.imgcorr_launch_count(self._h))
+
+    def _stream(self):
+        return ctypes.c_void_p(torch().cuda.current_stream(self.device).cuda_stream)
+
+    # -- calibration ------------------------------------------------------------------------
+    def _map_arg(self, arr):
+        """float32 [H][W] map as (pointer, on_device, keepalive)."""
+        if arr is None:
+            return None, 0, None
+        tt = torch()
+        if isinstance(arr, tt.Tensor):
+            t = arr.to(device=self.device, dtype=tt.float32).contiguous()
+            if tuple(t.shape) != (self.H, self.W):
+                raise ValueError('map shape %s != frame shape %s' % (tuple(t.shape), (self.H, self.W)))
+            return ctypes.c_void_p(t.data_ptr()), 1, t
+        a = np.ascontiguousarray(arr, dtype=np.float32)
+        if a.shape != (self.H, self.W):
+            a = np.ascontiguousarray(np.broadcast_to(a, (self.H, self.W)))
+        return a.ctypes.data_as(ctypes.c_void_p), 0, a
+
+    def set_dark(self, dark, ascent=None, exposure_time=0.0, depth_bits=16, token=None):
+        if token is not None and self._tokens.get('dark') == token:
+            return
+        p, dev, keep = self._map_arg(dark)
+        p2, dev2, keep2 = self._map_arg(ascent)
+        if keep is not None and keep2 is not None and dev != dev2:
+            raise ValueError('dark and ascent must both be host arrays or both device tensors')
+        _lib.check(self.lib.imgcorr_set_dark(self._h, p, p2, float(exposure_time), int(depth_bits), dev))
+        self.has_dark = dark is not None
+        self._tokens['dark'] = token
+
+    def set_flat(self, flat, token=None):
+        if token is not None and self._tokens.get('flat') == token:
+            return
+        p, dev, keep = self._map_arg(flat)
+        _lib.check(self.lib.imgcorr_set_flat(self._h, p, dev))
+        self.has_flat = flat is not None
+        self._tokens['flat'] = token
+
+    def set_lens(self, K, dist, P):
+        if K is None:
+            _lib.check(self.lib.imgcorr_set_lens(self._h, None, None, None))
+            self.has_lens = False
+            return
+        K = np.ascontiguousarray(np.asarray(K, np.float64).reshape(3, 3))
+        d = np.ascontiguousarray(np.asarray(dist, np.float64).ravel())
+        if d.size != 5:
+            raise ValueError('only the 5-term distortion model [k1,k2,p1,p2,k3] is supported, got %d terms' % d.size)
+        P = np.ascontiguousarray(np.asarray(P, np.float64)[:3, :3])
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(self.lib.imgcorr_set_lens(self._h, vp(K), vp(d), vp(P)))
+        self.has_lens = True
+
+    # -- helpers ----------------------------------------------------------------------------
+    def _frames(self, t):
+        tt = torch()
+        if not isinstance(t, tt.Tensor):
+            raise TypeError('expected a torch tensor on %s' % self.device)
+        if t.device != self.device:
+            raise ValueError('tensor on %s, engine on %s' % (t.device, self.device))
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        if t.dim() != 3 or tuple(t.shape[1:]) != (self.H, self.W):
+            raise ValueError('frames of shape %s do not match the engine (%d, %d)' % (tuple(t.shape), self.H, self.W))
+        return t.contiguous()
+
+    def _window(self, window):
+        if window is None:
+            return 0, 0, self.W, self.H
+        x, y, w, h = (int(v) for v in window)
+        return x, y, w, h
+
+    # -- kernels ----------------------------------------------------------------------------
+    def pointwise_median(self, raw, threshold=0.1, ksize=3, cond='>', flags=DO_DARK | DO_FLAT | DO_NAN_TO_NUM,
+                         out_dtype=None, want_mask=False, out=None):
+        """K1.  raw: [n,H,W] or [H,W] device tensor.  Returns (out, mask-or-None)."""
+        tt = torch()
+        squeeze = raw.dim() == 2
+        raw = self._frames(raw)
+        n = raw.shape[0]
+        rc = _dtype_code(raw.dtype)
+        if out_dtype is None:
+            out_dtype = tt.float64 if raw.dtype == tt.float64 else tt.float32
+        if out is None:
+            out = tt.empty((n, self.H, self.W), dtype=out_dtype, device=self.device)
+        mask = tt.zeros((n, self.H, self.W), dtype=tt.uint8, device=self.device) if want_mask else None
+        _lib.check(self.lib.imgcorr_pointwise_median(
+            self._h, ctypes.c_void_p(raw.data_ptr()), rc, ctypes.c_void_p(out.data_ptr()), _dtype_code(out.dtype),
+            ctypes.c_void_p(mask.data_ptr()) if mask is not None else None, n, float(threshold), int(ksize),
+            _lib.COND_GT if cond == '>' else _lib.COND_LT, int(flags), self._stream()))
+        if squeeze:
+            out = out[0]
+            mask = mask[0] if mask is not None else None
+        return out, mask
+
+    def undistort(self, src, out_dtype=None, border_value=0.0, window=None, out=None):
+        """K2 with the analytic map of the lens set by set_lens()."""
+        tt = torch()
+        squeeze = src.dim() == 2
+        src = self._frames(src)
+        n = src.shape[0]
+        x0, y0, ow, oh = self._window(window)
+        if out_dtype is None:
+            out_dtype = src.dtype
+        if out is None:
+            out = tt.empty((n, oh, ow), dtype=out_dtype, device=self.device)
+        _lib.check(self.lib.imgcorr_undistort(
+            self._h, ctypes.c_void_p(src.data_ptr()), _dtype_code(src.dtype), ctypes.c_void_p(out.data_ptr()),
+            _dtype_code(out.dtype), n, float(border_value), x0, y0, ow, oh, self._stream()))
+        return out[0] if squeeze else out
+
+    def remap(self, src, mapx, mapy, border_value=0.0, out_dtype=None):
+        """K2 with caller-supplied float32 maps [H,W] (device tensors)."""
+        tt = torch()
+        squeeze = src.dim() == 2
+        src = self._frames(src)
+        n = src.shape[0]
+        mapx = mapx.to(device=self.device, dtype=tt.float32).contiguous()
+        mapy = mapy.to(device=self.device, dtype=tt.float32).contiguous()
+        if tuple(mapx.shape) != (self.H, self.W) or tuple(mapy.shape) != (self.H, self.W):
+            raise ValueError('maps must be [H,W]')
+        out = tt.empty((n, self.H, self.W), dtype=out_dtype or src.dtype, device=self.device)
+        _lib.check(self.lib.imgcorr_remap(
+            self._h, ctypes.c_void_p(src.data_ptr()), _dtype_code(src.dtype), ctypes.c_void_p(out.data_ptr()),
+            _dtype_code(out.dtype), n, ctypes.c_void_p(mapx.data_ptr()), ctypes.c_void_p(mapy.data_ptr()),
+            float(border_value), self._stream()))
+        return out[0] if squeeze else out
+
+    def undistort_maps(self):
+        tt = torch()
+        mapx = tt.empty((self.H, self.W), dtype=tt.float32, device=self.device)
+        mapy = tt.empty_like(mapx)
+        _lib.check(self.lib.imgcorr_undistort_maps(self._h, ctypes.c_void_p(mapx.data_ptr()),
+                                                   ctypes.c_void_p(mapy.data_ptr()), self._stream()))
+        return mapx, mapy
+
+    def correct_batch(self, raw, threshold=0.1, ksize=3, flags=DO_DARK | DO_FLAT | DO_NAN_TO_NUM, use_lens=True,
+                      border_value=0.0, window=None, out_dtype=None, out=None):
+        """K1 -> K2 for every frame of a device-resident batch [n,H,W]."""
+        tt = torch()
+        squeeze = raw.dim() == 2
+        raw = self._frames(raw)
+        n = raw.shape[0]
+        lens = bool(use_lens and self.has_lens)
+        x0, y0, ow, oh = self._window(window if lens else None)
+        if out is None:
+            out = tt.empty((n, oh, ow), dtype=out_dtype or tt.float32, device=self.device)
+        _lib.check(self.lib.imgcorr_correct_batch(
+            self._h, ctypes.c_void_p(raw.data_ptr()), _dtype_code(raw.dtype), ctypes.c_void_p(out.data_ptr()),
+            _dtype_code(out.dtype), n, float(threshold), int(ksize), int(flags), int(lens), float(border_value),
+            x0, y0, ow, oh, self._stream()))
+        return out[0] if squeeze else out
+
+    def correct_host(self, raw, out=None, threshold=0.1, ksize=3, flags=DO_DARK | DO_FLAT | DO_NAN_TO_NUM,
+                     use_lens=True, border_value=0.0, window=None, out_dtype=np.float32):
+        """The chain on HOST numpy frames [n,H,W] (uint8/uint16/float32): pinned staging, H2D, kernels and
+        D2H of consecutive frames overlap inside the library.  Synchronous."""
+        squeeze = raw.ndim == 2
+        raw = np.ascontiguousarray(raw)
+        if squeeze:
+            raw = raw[None]
+        if raw.shape[1:] != (self.H, self.W):
+            raise ValueError('frames of shape %s do not match the engine (%d, %d)' % (raw.shape, self.H, self.W))
+        n = raw.shape[0]
+        lens = bool(use_lens and self.has_lens)
+        x0, y0, ow, oh = self._window(window if lens else None)
+        if out is None:
+            out = np.empty((n, oh, ow), dtype=out_dtype)
+        if not out.flags.c_contiguous or out.shape != (n, oh, ow):
+            raise ValueError('out must be C-contiguous of shape %s' % ((n, oh, ow),))
+        _lib.check(self.lib.imgcorr_correct_host(
+            self._h, raw.ctypes.data_as(ctypes.c_void_p), NP_CODES[raw.dtype], out.ctypes.data_as(ctypes.c_void_p),
+            NP_CODES[out.dtype], n, float(threshold), int(ksize), int(flags), int(lens), float(border_value),
+            x0, y0, ow, oh))
+        return out[0] if squeeze else out
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from imgcorr_host_alloc (freed with the array)."""
+    lib = _lib.lib()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = ctypes.c_void_p()
+    _lib.check(lib.imgcorr_host_alloc(nbytes, ctypes.byref(p)))
+
+    class _Owner(object):
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.imgcorr_host_free(self.ptr)
+            except Exception:
+                pass
+
+    buf = (ctypes.c_char * max(nbytes, 1)).from_address(p.value)
+    buf._owner = _Owner(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr
+
+
+_ENGINES = {}
+
+
+def get_engine(height, width, device=None):
+    tt = require_cuda()
+    idx = tt.cuda.current_device() if device is None else tt.device('cuda', device).index
+    key = (idx, int(height), int(width))
+    e = _ENGINES.get(key)
+    if e is None or e._h is None:
+        e = _ENGINES[key] = Engine(height, width, idx)
+    return e

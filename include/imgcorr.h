@@ -1,0 +1,152 @@
+/* imgcorr.h — C ABI of libimgcorr.so: the B200 (sm_100a) implementation of the per-frame
+ * camera-correction path of radjkarl/imgProcessor,
+ *
+ *     imgProcessor.camera.CameraCalibration.correct()      camera/CameraCalibration.py:351-459
+ *
+ * The reference is pure Python and has no FFI of its own: this header is the boundary a
+ * maintainer would bind (ctypes stub in INTEGRATION.md) to route that one path to the GPU.
+ * Every entry point cites the reference lines it replaces (paths relative to
+ * /root/reference/imgProcessor/).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; all images are dense row-major [n_frames][H][W].
+ *   - "dev" pointers are device pointers owned by the caller (e.g. torch tensor data_ptr()),
+ *     "host" pointers are host memory; the library owns only its per-context copies of the
+ *     calibration maps, scratch frames and (for the *_host entry points) pinned staging rings.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream). Calls are
+ *     asynchronous with respect to the host unless stated otherwise.
+ *   - every function returns IMGCORR_OK (0) or a negative imgcorr_status; the message of the
+ *     last failure on the calling thread is returned by imgcorr_last_error().  Nothing aborts,
+ *     nothing throws, and there is NO CPU fallback: without a CUDA device every compute call
+ *     fails with IMGCORR_ERR_CUDA.
+ */
+#ifndef IMGCORR_H
+#define IMGCORR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMGCORR_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define IMGCORR_API __attribute__((visibility("default")))
+#else
+#define IMGCORR_API
+#endif
+
+typedef struct imgcorr_ctx imgcorr_ctx;
+
+typedef enum imgcorr_status {
+    IMGCORR_OK = 0,
+    IMGCORR_ERR_INVALID = -1, /* bad argument (shape, dtype combination, null pointer, ...) */
+    IMGCORR_ERR_CUDA = -2,    /* a CUDA runtime / driver call failed (message has the detail) */
+    IMGCORR_ERR_STATE = -3,   /* e.g. undistort requested but no lens set */
+    IMGCORR_ERR_NOMEM = -4
+} imgcorr_status;
+
+typedef enum imgcorr_dtype { IMGCORR_U8 = 0, IMGCORR_U16 = 1, IMGCORR_F32 = 2, IMGCORR_F64 = 3 } imgcorr_dtype;
+
+/* medianThreshold(condition=...)  filters/medianThreshold.py:21-24 */
+typedef enum imgcorr_cond { IMGCORR_COND_GT = 0, IMGCORR_COND_LT = 1 } imgcorr_cond;
+
+/* stage switches of the fused pointwise step */
+enum {
+    IMGCORR_DO_DARK = 1,       /* image -= bg                           CameraCalibration.py:502      */
+    IMGCORR_DO_FLAT = 2,       /* image[flat != 0] /= flat[flat != 0]   CameraCalibration.py:525-526  */
+    IMGCORR_DO_NAN_TO_NUM = 4  /* image = np.nan_to_num(image)          CameraCalibration.py:561      */
+};
+
+/* imgcorr_set_option keys */
+enum {
+    IMGCORR_OPT_K1_VARIANT = 1, /* 0 auto, 1 generic loads, 2 TMA-staged (fails if not eligible) */
+    IMGCORR_OPT_K2_VARIANT = 2, /* reserved */
+    IMGCORR_OPT_HOST_SLOTS = 3  /* depth of the pinned / device staging ring of the *_host calls (default 4) */
+};
+
+IMGCORR_API const char* imgcorr_last_error(void);
+IMGCORR_API int imgcorr_version(void);
+
+/* Number of CUDA devices visible, or a negative status. */
+IMGCORR_API int imgcorr_device_count(void);
+
+/* ---- context: one per (device, frame shape).  Holds the device copies of the calibration maps
+ * that CameraCalibration keeps in self.coeffs (camera/CameraCalibration.py:63-81). -------------- */
+IMGCORR_API int imgcorr_ctx_create(int device, int height, int width, imgcorr_ctx** out_ctx);
+IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* ctx);
+IMGCORR_API int imgcorr_set_option(imgcorr_ctx* ctx, int key, int value);
+/* kernels launched by this context so far (bench.py's gpu_launches claim) */
+IMGCORR_API long long imgcorr_launch_count(const imgcorr_ctx* ctx);
+
+/* Dark current (calcDarkCurrent, camera/CameraCalibration.py:504-518).
+ *   ascent == NULL : bg = dark                                   (entry built by addDarkCurrent(arr), :516)
+ *   ascent != NULL : bg = dark + ascent * exposure_time, clipped to 2**depth_bits - 1, evaluated in
+ *                    float64 per pixel                           (legacy tuple entry, :507-513)
+ * Maps are float32 [H][W]; `on_device` != 0 means the pointers are device pointers (copied D2D),
+ * otherwise host pointers.  dark == NULL removes the calibration. Synchronous. */
+IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* ctx, const float* dark, const float* ascent, double exposure_time,
+                     int depth_bits, int on_device);
+/* Flat field (camera/CameraCalibration.py:520-526).  flat == NULL removes it. Synchronous. */
+IMGCORR_API int imgcorr_set_flat(imgcorr_ctx* ctx, const float* flat, int on_device);
+/* Lens (camera/LensDistortion.py:342-358): K = cameraMatrix (3x3 row-major), dist = [k1,k2,p1,p2,k3]
+ * (camera/LensDistortion.py:370,380), P = newCameraMatrix from cv2.getOptimalNewCameraMatrix (:350-353,
+ * computed by the host wrapper exactly as the reference does).  K == NULL removes the lens. */
+IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* ctx, const double K[9], const double dist[5], const double P[9]);
+
+/* ---- K1: fused dark / flat / nan_to_num / NxN median-threshold ---------------------------------
+ * Replaces _correctDarkCurrent + _correctVignetting + _correctArtefacts
+ * (camera/CameraCalibration.py:476-526, 556-563) and medianThreshold (filters/medianThreshold.py:7-30).
+ *   raw_dev   [n][H][W] of raw_dtype (U8, U16, F32, F64)
+ *   out_dev   [n][H][W] of out_dtype: F32 for U8/U16/F32 input, the input dtype itself (direct
+ *             medianThreshold keeps the image dtype), F64 for F32/F64 input
+ *   mask_dev  [n][H][W] uint8 `indices` of medianThreshold, or NULL
+ *   ksize     0 (pointwise only), 3 or 5;  threshold <= 0 is treated as ksize 0 (medianThreshold.py:16)
+ *   flags     IMGCORR_DO_* ; dark / flat are applied only if set in the context as well */
+IMGCORR_API int imgcorr_pointwise_median(imgcorr_ctx* ctx, const void* raw_dev, int raw_dtype, void* out_dev, int out_dtype,
+                             uint8_t* mask_dev, int n_frames, double threshold, int ksize, int cond, int flags,
+                             void* stream);
+
+/* ---- K2: undistortion ---------------------------------------------------------------------------
+ * Replaces LensDistortion.correct (camera/LensDistortion.py:316-330): analytic Brown-Conrady map
+ * (cv2.initUndistortRectifyMap semantics, float64 -> float32) + cv2.remap(INTER_LINEAR,
+ * BORDER_CONSTANT, border_value) with OpenCV's 5-bit fixed-point coordinates and weight table.
+ *   src_dev [n][H][W], dst_dev [n][oh][ow]; (x0,y0,ow,oh) = output window in full-frame coordinates:
+ *   (0,0,W,H) for keepSize=True, the roi for keepSize=False (:327-329).
+ *   dtype pairs: F32->F32, F32->F64 (widening for the float64 API), F64->F64, U16->U16, U8->U8. */
+IMGCORR_API int imgcorr_undistort(imgcorr_ctx* ctx, const void* src_dev, int src_dtype, void* dst_dev, int dst_dtype,
+                      int n_frames, double border_value, int x0, int y0, int ow, int oh, void* stream);
+/* cv2.remap with caller-supplied float32 maps [H][W] (LensDistortion.distortImage, :332-340). */
+IMGCORR_API int imgcorr_remap(imgcorr_ctx* ctx, const void* src_dev, int src_dtype, void* dst_dev, int dst_dtype, int n_frames,
+                  const float* mapx_dev, const float* mapy_dev, double border_value, void* stream);
+/* getUndistortRectifyMap (camera/LensDistortion.py:342-358): writes mapx, mapy float32 [H][W]. */
+IMGCORR_API int imgcorr_undistort_maps(imgcorr_ctx* ctx, float* mapx_dev, float* mapy_dev, void* stream);
+
+/* ---- the chain: K1 -> K2 per frame, device resident --------------------------------------------
+ * CameraCalibration.correct() for n independent frames (camera/CameraCalibration.py:351-459, single
+ * image branch; a stack of frames is a batch here, not the STE average of :385-406).
+ *   threshold > 0 : median-threshold with ksize (3 in correct(), :556-563) after nan_to_num
+ *   use_lens      : apply K2 if a lens is set (missing lens -> frames pass through, :570-575)
+ *   out_dtype     : F32 or F64 (float64 is what the reference returns, :459) */
+IMGCORR_API int imgcorr_correct_batch(imgcorr_ctx* ctx, const void* raw_dev, int raw_dtype, void* out_dev, int out_dtype,
+                          int n_frames, double threshold, int ksize, int flags, int use_lens, double border_value,
+                          int x0, int y0, int ow, int oh, void* stream);
+
+/* Same chain with HOST buffers: frames are staged through a ring of pinned buffers, H2D copy,
+ * kernels and D2H copy of consecutive frames overlap on three streams.  Synchronous: returns
+ * when out_host is complete.  Fastest when raw_host / out_host come from imgcorr_host_alloc
+ * (or are otherwise page-locked). */
+IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* ctx, const void* raw_host, int raw_dtype, void* out_host, int out_dtype,
+                         int n_frames, double threshold, int ksize, int flags, int use_lens, double border_value,
+                         int x0, int y0, int ow, int oh);
+
+/* page-locked host memory for the *_host entry points */
+IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr);
+IMGCORR_API int imgcorr_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMGCORR_H */

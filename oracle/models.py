@@ -201,6 +201,9 @@ def remap_model(src, mapx, mapy, border_value=0):
     assert src.ndim == 2
     ix, iy, fx, fy = fixed_point_coords(mapx, mapy)
     w00, w01, w10, w11 = bilinear_weights_f32(fx, fy)
+    H, W = src.shape
+    # a 2x2 window entirely outside the image yields the border value itself (not a blend of it)
+    outside = (ix >= W) | (ix + 1 < 0) | (iy >= H) | (iy + 1 < 0)
     if src.dtype == np.uint8:
         sc = float(1 << INTER_REMAP_COEF_BITS)
         iw = [np.rint(w.astype(np.float64) * sc).astype(np.int64) for w in (w00, w01, w10, w11)]
@@ -209,7 +212,7 @@ def remap_model(src, mapx, mapy, border_value=0):
         acc = (_gather(s, ix, iy, b) * iw[0] + _gather(s, ix + 1, iy, b) * iw[1]
                + _gather(s, ix, iy + 1, b) * iw[2] + _gather(s, ix + 1, iy + 1, b) * iw[3])
         r = (acc + (1 << (INTER_REMAP_COEF_BITS - 1))) >> INTER_REMAP_COEF_BITS
-        return np.clip(r, 0, 255).astype(np.uint8)
+        return np.where(outside, b, np.clip(r, 0, 255)).astype(np.uint8)
     if src.dtype == np.float64:
         acc_t = np.float64
         b = np.float64(border_value)
@@ -224,6 +227,7 @@ def remap_model(src, mapx, mapy, border_value=0):
     with np.errstate(over='ignore', invalid='ignore'):
         r = ((_gather(s, ix, iy, b) * w00 + _gather(s, ix + 1, iy, b) * w01)
              + _gather(s, ix, iy + 1, b) * w10) + _gather(s, ix + 1, iy + 1, b) * w11
+    r = np.where(outside, b, r)
     if src.dtype == np.uint16:
         return np.clip(np.rint(r), 0, 65535).astype(np.uint16)
     return r.astype(src.dtype)

@@ -1,0 +1,59 @@
+"""The C-ABI library loads on a box without a GPU, exports every symbol include/imgcorr.h declares,
+and fails loudly (status + message, no abort, no fallback) when asked to compute without a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'imgcorr.h')).read()
+    return sorted(set(re.findall(r'IMGCORR_API[^;(]*?\b(imgcorr_\w+)\s*\(', src)))
+
+
+def test_header_declares_the_expected_surface():
+    names = _declared()
+    for must in ('imgcorr_ctx_create', 'imgcorr_pointwise_median', 'imgcorr_undistort', 'imgcorr_correct_batch',
+                 'imgcorr_correct_host', 'imgcorr_last_error'):
+        assert must in names
+    assert len(names) >= 18
+
+
+def test_library_exports_every_declared_symbol():
+    from imgprocessor_b200 import _lib
+    handle = _lib.lib()
+    for name in _declared():
+        assert hasattr(handle, name), name
+        assert name in _lib.SIGNATURES, 'ctypes signature missing for %s' % name
+    assert set(_lib.SIGNATURES) == set(_declared())
+    assert handle.imgcorr_version() == 100
+
+
+def test_no_device_means_loud_failure_not_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('this check is for the CPU box')
+    from imgprocessor_b200 import _lib
+    handle = _lib.lib()
+    ctx = ctypes.c_void_p()
+    st = handle.imgcorr_ctx_create(0, 16, 16, ctypes.byref(ctx))
+    assert st == _lib.ERR_CUDA and not ctx.value
+    assert b'cuda' in handle.imgcorr_last_error().lower()
+    import numpy as np
+    from imgprocessor_b200.filters import medianThreshold
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        medianThreshold(np.ones((8, 8), np.float32), 0.1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'imgprocessor_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', txt, re.M), os.path.join(dirpath, f)
+                assert 'scipy' not in txt or f in ('medianThreshold.py', 'CameraCalibration.py', 'LensDistortion.py', '__init__.py',
+                                                   'k1_pointwise_median.cu', 'imgcorr_core.cuh', 'synth.py'), f

@@ -1,0 +1,494 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes -> libimgcorr.so), against the
+oracle on the same seeded inputs and against the golden outputs of the unmodified reference.
+Bars (BASELINE.json north star): median + mask bit-exact; pointwise float32 <= 1 ulp of the float64
+reference (we require 0 ulp: correctly rounded); remap bit-exact given the same fixed-point coordinates;
+end to end vs the float64 reference <= 1e-3 of full scale (we require 1e-5)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, ulp_diff_f32
+from imgprocessor_b200 import synth
+from oracle import models, refpath
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+
+
+@pytest.fixture(scope='module')
+def ip():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    import imgprocessor_b200 as pkg
+    from imgprocessor_b200 import engine, _lib
+    pkg.engine_mod, pkg.lib_mod = engine, _lib
+    return pkg
+
+
+def _eng(ip, H, W, variant=0):
+    e = ip.engine_mod.get_engine(H, W)
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, variant)
+    return e
+
+
+def _case(H, W, seed, dtype=np.uint16):
+    raw = synth.scene(H, W, seed, dtype)
+    dark = synth.dark_map(H, W, seed)
+    flat = synth.flat_map(H, W, seed, p_zero=5e-3)
+    return raw, dark, flat
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+SHAPES = [(1, 1), (2, 3), (5, 4), (33, 130), (96, 128), (70, 257), (300, 520), (257, 1024)]
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+@pytest.mark.parametrize('dtype', [np.uint8, np.uint16, np.float32])
+@pytest.mark.parametrize('ksize', [3, 5])
+def test_k1_bit_exact_generic(ip, shape, dtype, ksize):
+    H, W = shape
+    raw, dark, flat = _case(H, W, 3, dtype)
+    e = _eng(ip, H, W, 1)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    out, mask = e.pointwise_median(_dev(raw), 0.1, ksize, want_mask=True)
+    x = models.pointwise_model(raw, dark, flat, nan_to_num=True)
+    want, wmask = models.median_threshold_model(x, 0.1, ksize)
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+
+
+@pytest.mark.parametrize('shape', [(5, 8), (33, 136), (96, 128), (70, 264), (300, 520), (257, 1024), (64, 4096)])
+@pytest.mark.parametrize('dtype', [np.uint16, np.float32])
+@pytest.mark.parametrize('ksize', [3, 5])
+def test_k1_bit_exact_tma(ip, shape, dtype, ksize):
+    H, W = shape
+    raw, dark, flat = _case(H, W, 4, dtype)
+    e = _eng(ip, H, W, 2)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    out, mask = e.pointwise_median(_dev(raw), 0.1, ksize, want_mask=True)
+    x = models.pointwise_model(raw, dark, flat, nan_to_num=True)
+    want, wmask = models.median_threshold_model(x, 0.1, ksize)
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    # partial calibrations through the TMA path as well
+    e.set_dark(None)
+    out, _ = e.pointwise_median(_dev(raw), 0.1, ksize)
+    want, _ = models.median_threshold_model(models.pointwise_model(raw, None, flat, True), 0.1, ksize)
+    assert np.array_equal(out.cpu().numpy(), want)
+    e.set_flat(None)
+    out, _ = e.pointwise_median(_dev(raw), 0.1, ksize)
+    want, _ = models.median_threshold_model(models.pointwise_model(raw, None, None, True), 0.1, ksize)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_k1_tma_refused_when_not_eligible(ip):
+    e = _eng(ip, 33, 130, 2)
+    with pytest.raises(ip.lib_mod.ImgcorrError):
+        e.pointwise_median(_dev(np.zeros((33, 130), np.uint16)), 0.1, 3)
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
+def test_k1_multi_frame_batch(ip):
+    H, W, n = 70, 264, 5
+    e = _eng(ip, H, W, 0)
+    _, dark, flat = _case(H, W, 1)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    frames = np.stack([synth.scene(H, W, 10 + i, np.uint16) for i in range(n)])
+    for variant in (1, 2):
+        e.set_option(ip.lib_mod.OPT_K1_VARIANT, variant)
+        out, mask = e.pointwise_median(_dev(frames), 0.1, 3, want_mask=True)
+        for i in range(n):
+            want, wmask = models.median_threshold_model(models.pointwise_model(frames[i], dark, flat, True), 0.1, 3)
+            assert np.array_equal(out[i].cpu().numpy(), want)
+            assert np.array_equal(mask[i].cpu().numpy().astype(bool), wmask)
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
+def test_k1_pointwise_zero_ulp(ip):
+    H, W = 64, 96
+    raw, dark, flat = _case(H, W, 9)
+    flat[3, 3] = np.float32(1e-42)
+    flat[4, 4] = np.float32(-2.0)
+    e = _eng(ip, H, W)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    out, _ = e.pointwise_median(_dev(raw), 0.0, 0, flags=3)
+    x = refpath.to_float_image(raw)
+    refpath.correct_dark_current(x, dark)
+    refpath.correct_vignetting(x, flat)
+    with np.errstate(over='ignore'):
+        ref32 = x.astype(np.float32)
+    got = out.cpu().numpy()
+    fin = np.isfinite(ref32)
+    assert ulp_diff_f32(got[fin], ref32[fin]).max() == 0          # north star asks for <= 1
+    assert np.array_equal(got, ref32)
+    out, _ = e.pointwise_median(_dev(raw), 0.0, 0, flags=7)
+    assert out[3, 3].item() == np.finfo(np.float32).max
+    # float64 widening output
+    out, _ = e.pointwise_median(_dev(raw), 0.0, 0, flags=3, out_dtype=torch.float64)
+    assert np.array_equal(out.cpu().numpy(), ref32.astype(np.float64))
+
+
+def test_k1_legacy_linear_dark(ip):
+    g = load_golden('correct_u16_legacy_dark')
+    offs, asc = g['offs'].astype(np.float32), g['ascent'].astype(np.float32)
+    H, W = offs.shape
+    e = _eng(ip, H, W)
+    e.set_dark(offs, asc, float(g['exposure_time']), 16)
+    e.set_flat(None)
+    out, _ = e.pointwise_median(_dev(g['raw']), 0.0, 0, flags=1)
+    want = models.pointwise_model(g['raw'], offs, None, False, dark_ascent=asc, exposure_time=float(g['exposure_time']))
+    assert np.array_equal(out.cpu().numpy(), want)
+    out, _ = e.pointwise_median(_dev(g['raw']), 0.1, 3, flags=5)
+    want, _ = models.median_threshold_model(models.nan_to_num_f32(want), 0.1, 3)
+    assert np.array_equal(out.cpu().numpy(), want)
+    # and against the float64 reference output itself
+    assert np.abs(out.cpu().numpy() - g['out']).max() / 65535.0 < 1e-5
+
+
+@pytest.mark.parametrize('name', ['median_u16_s3_gt', 'median_u16_s3_lt', 'median_u16_s5_gt', 'median_u16_s5_lt',
+                                  'median_f32_s3_gt', 'median_f32_s3_lt', 'median_f32_s5_gt', 'median_f32_s5_lt'])
+def test_medianThreshold_api_vs_reference_golden(ip, name):
+    g = load_golden(name)
+    size = 3 if '_s3_' in name else 5
+    cond = '>' if name.endswith('gt') else '<'
+    img = g['img'].copy()
+    out, ind = ip.medianThreshold(img, threshold=0.1, size=size, condition=cond, copy=True)
+    assert out is not img and np.array_equal(img, g['img'])
+    assert out.dtype == g['out'].dtype and np.array_equal(out, g['out'])
+    assert ind.dtype == bool and np.array_equal(ind, g['ind'])
+    same, ind2 = ip.medianThreshold(img, threshold=0.1, size=size, condition=cond, copy=False)
+    assert same is img and np.array_equal(img, g['out']) and np.array_equal(ind2, g['ind'])
+    untouched, none = ip.medianThreshold(img, threshold=0)
+    assert untouched is img and none is None
+
+
+def test_medianThreshold_zero_medians_f64_and_extremes(ip):
+    g = load_golden('median_f32_zeros')
+    out, ind = ip.medianThreshold(g['img'], float(g['threshold']), 3)
+    assert np.array_equal(out, g['out']) and np.array_equal(ind, g['ind'])
+    rng = np.random.default_rng(4)
+    img = rng.normal(1000, 300, (40, 50))
+    img[rng.random(img.shape) < 0.01] *= 5
+    for size in (3, 5):
+        out, ind = ip.medianThreshold(img, 0.2, size)
+        want, wmask = models.median_threshold_model(img, 0.2, size)
+        assert out.dtype == np.float64 and np.array_equal(out, want) and np.array_equal(ind, wmask)
+    ext = np.array([[3e38, -3e38, 1e-40, 0, 5], [1e30, -1e30, 7, 1, 2], [0, 0, 0, 0, 0]], np.float32)
+    for thr in (0.1, 5.0):
+        out, ind = ip.medianThreshold(ext, thr, 3)
+        want, wmask = models.median_threshold_model(ext, thr, 3)
+        assert np.array_equal(ind, wmask) and np.array_equal(out, want)
+
+
+def test_predicate_guard_band(ip):
+    """pixels engineered to sit on the threshold from both sides, many seeds, one launch per seed"""
+    for seed in range(40):
+        rng = np.random.default_rng(seed)
+        H, W = 24, 40
+        thr = float(rng.choice([0.01, 0.1, 0.3, 1.0, 1.5]))
+        img = (rng.random((H, W)) * 100 + 1).astype(np.float32)
+        med = models.median_filter_reflect(img, 3)
+        for _ in range(40):
+            y, x = rng.integers(0, H), rng.integers(0, W)
+            b = np.float64(med[y, x])
+            img[y, x] = np.float32(b * (1 + thr * rng.choice([-1, 1])) * (1 + rng.choice([-1, 0, 1]) * 6e-8))
+        for cond in ('>', '<'):
+            out, ind = ip.medianThreshold(img, thr, 3, cond)
+            want, wmask = models.median_threshold_model(img, thr, 3, cond)
+            assert np.array_equal(ind, wmask) and np.array_equal(out, want)
+
+
+# ---------------------------------------------------------------------------- K2
+@pytest.mark.parametrize('tag', ['moderate', 'strong', 'realistic'])
+def test_maps_vs_reference_golden(ip, tag):
+    g = load_golden('maps_' + tag)
+    H, W = (int(v) for v in g['shape'])
+    l = ip.LensDistortion({})
+    l._coeffs['cameraMatrix'], l._coeffs['distortionCoeffs'] = g['K'], g['dist']
+    mx, my = l.getUndistortRectifyMap(W, H)
+    assert mx.dtype == np.float32 and tuple(l.roi) == tuple(g['roi'])
+    for a, b in zip(models.fixed_point_coords(mx, my), models.fixed_point_coords(g['mapx'], g['mapy'])):
+        assert np.array_equal(a, b)
+    assert (mx != g['mapx']).mean() < 1e-3 and (my != g['mapy']).mean() < 1e-3
+    assert np.abs(mx.astype(np.float64) - g['mapx']).max() < 2e-4
+
+
+@pytest.mark.parametrize('tag', ['u8', 'u16', 'f32', 'f64'])
+@pytest.mark.parametrize('keep', [0, 1])
+def test_LensDistortion_correct_vs_reference_golden(ip, tag, keep):
+    g = load_golden('lens_%s_keep%d' % (tag, keep))
+    l = ip.LensDistortion({})
+    l._coeffs['cameraMatrix'], l._coeffs['distortionCoeffs'] = g['K'], g['dist']
+    out = l.correct(g['img'], keepSize=bool(keep), borderValue=float(g['border']))
+    assert out.dtype == g['out'].dtype and out.shape == g['out'].shape
+    assert tuple(l.roi) == tuple(g['roi'])
+    assert np.array_equal(out, g['out'])          # bit-exact incl. the analytic map on this fixture
+    assert l.img is out
+
+
+@pytest.mark.parametrize('dtype', [np.uint8, np.uint16, np.float32, np.float64])
+def test_remap_explicit_maps_vs_model(ip, dtype):
+    rng = np.random.default_rng(3)
+    H, W = 70, 90
+    if np.dtype(dtype).kind == 'u':
+        src = rng.integers(0, np.iinfo(dtype).max + 1, (H, W)).astype(dtype)
+    else:
+        src = ((rng.random((H, W)) - 0.3) * 4000).astype(dtype)
+    mapx = np.arange(W, dtype=np.float32)[None, :] + rng.normal(0, 4, (H, W)).astype(np.float32)
+    mapy = np.arange(H, dtype=np.float32)[:, None] + rng.normal(0, 4, (H, W)).astype(np.float32)
+    mapx[0, :6] = [-1.0, -0.5, W - 1, W - 0.5, W, 1e9]
+    mapy[1, :4] = [-1.0, H - 1, H, -1e9]
+    mapx[2, :3] = [np.nan, np.inf, -np.inf]
+    mapx[3, :4] = np.float32(10) + np.array([0.5, 1.5, 2.5, 3.5], np.float32) / np.float32(32)
+    e = _eng(ip, H, W)
+    for border in (0, 7, 0.1234567):
+        out = e.remap(_dev(src), _dev(mapx), _dev(mapy), border).cpu().numpy()
+        assert out.dtype == src.dtype
+        assert np.array_equal(out, models.remap_model(src, mapx, mapy, border))
+    if dtype == np.float32:
+        wide = e.remap(_dev(src), _dev(mapx), _dev(mapy), 0.0, out_dtype=torch.float64).cpu().numpy()
+        assert np.array_equal(wide, models.remap_model(src, mapx, mapy, 0).astype(np.float64))
+
+
+def test_undistort_multi_frame_and_window(ip):
+    H, W, n = 125, 166, 4
+    p = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    mapx, mapy, P, roi = refpath.undistort_rectify_map(K, d, W, H)
+    e = _eng(ip, H, W)
+    e.set_lens(K, d, P)
+    frames = np.stack([synth.scene(H, W, 20 + i, np.float32) for i in range(n)])
+    mx, my = (m.cpu().numpy() for m in e.undistort_maps())
+    full = e.undistort(_dev(frames)).cpu().numpy()
+    x, y, w, h = (int(v) for v in roi)
+    crop = e.undistort(_dev(frames), window=(x, y, w, h)).cpu().numpy()
+    for i in range(n):
+        want = models.remap_model(frames[i], mx, my, 0.0)
+        assert np.array_equal(full[i], want)
+        assert np.array_equal(crop[i], want[y:y + h, x:x + w])
+    with pytest.raises(ip.lib_mod.ImgcorrError):
+        e.undistort(_dev(frames), window=(0, 0, W + 1, H))
+
+
+# ---------------------------------------------------------------------------- the chain, reference API
+def _cal(ip, g, lens=True):
+    cal = ip.CameraCalibration()
+    if 'dark' in g:
+        cal.addDarkCurrent(g['dark'])
+    if 'flat' in g:
+        cal.addFlatField(g['flat'])
+    if lens and 'K' in g:
+        l = ip.LensDistortion({})
+        l._coeffs['cameraMatrix'], l._coeffs['distortionCoeffs'] = g['K'], g['dist']
+        l._coeffs['shape'] = g['raw'].shape
+        cal.addLens(l)
+    return cal
+
+
+def _quiet(fn, *a, **k):
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        r = fn(*a, **k)
+    return r, buf.getvalue()
+
+
+@pytest.mark.parametrize('keep', [1, 0])
+def test_correct_vs_unmodified_reference(ip, keep):
+    g = load_golden('correct_u16_keep%d' % keep)
+    cal = _cal(ip, g)
+    raw = g['raw'].copy()
+    out, log = _quiet(cal.correct, raw, threshold=0.1, keep_size=bool(keep))
+    assert np.array_equal(raw, g['raw'])                          # input never mutated
+    assert out.dtype == np.float64 and out.shape == g['out'].shape
+    assert log == str(g['log'])                                   # same progress lines
+    ok = np.abs(g['out']) < 1e6                                   # denormal-flat pixel overflows float32
+    assert (~ok).sum() <= 4
+    assert np.abs(out[ok] - g['out'][ok]).max() / 65535.0 < 1e-5  # north star bar: 1e-3
+    # bit-exact against the float32 staged oracle chain
+    mx, my = models.undistort_map_model(g['K'], g['dist'], refpath.undistort_rectify_map(g['K'], g['dist'], 128, 96)[2], 128, 96)
+    l = cal.getLens(None, None)
+    gmx, gmy = l.getUndistortRectifyMap(128, 96)
+    want, _ = models.correct_chain_f32(g['raw'], g['dark'], g['flat'], 0.1, 3, mapxy=(gmx, gmy))
+    if not keep:
+        x, y, w, h = (int(v) for v in l.roi)
+        want = want[y:y + h, x:x + w]
+    assert np.array_equal(out, want.astype(np.float64))
+    # last_img: the dark+flat corrected, pre-median image
+    li = cal.last_img
+    fin = np.isfinite(g['last_img']) & (np.abs(g['last_img']) < 3e38)
+    assert np.array_equal(li[fin], g['last_img'][fin].astype(np.float32).astype(np.float64))
+    assert np.array_equal(cal.temp['bg'], g['bg'])
+
+
+def test_correct_partial_calibrations_and_thr0(ip):
+    g = load_golden('correct_f32_thr0')
+    out, log = _quiet(_cal(ip, g).correct, g['raw'], threshold=0)
+    assert log == str(g['log'])
+    fin = np.isfinite(g['out']) & (np.abs(g['out']) < 1e6)
+    assert np.abs(out[fin] - g['out'][fin]).max() / 4095.0 < 1e-5
+    g = load_golden('correct_f32_flat_only')
+    out, log = _quiet(_cal(ip, g).correct, g['raw'], threshold=0.25)
+    assert log == str(g['log'])
+    ok = np.abs(g['out']) < 1e6
+    assert np.abs(out[ok] - g['out'][ok]).max() / 4095.0 < 1e-5
+    g = load_golden('correct_u16_nothing')
+    out, log = _quiet(ip.CameraCalibration().correct, g['raw'], threshold=0.1)
+    assert log == str(g['log'])
+    assert np.array_equal(out, g['out'])          # integers: float32 chain == float64 chain exactly
+
+
+def test_correct_legacy_tuple_dark_and_dates(ip):
+    import time
+    g = load_golden('correct_u16_legacy_dark')
+    cal = ip.CameraCalibration()
+    cal.coeffs['dark current'].append((time.localtime(), '', (g['offs'].copy(), g['ascent'].copy()), None))
+    cal.coeffs['shape'] = g['raw'].shape
+    out, log = _quiet(cal.correct, g['raw'], exposure_time=float(g['exposure_time']), threshold=0.1)
+    assert log == str(g['log'])
+    assert np.abs(out - g['out']).max() / 65535.0 < 1e-5
+    # exposure_time=None with a tuple entry: TypeError swallowed, stage skipped
+    out, log = _quiet(cal.correct, g['raw'], threshold=0)
+    assert 'Error:' in log and np.array_equal(out, g['raw'].astype(np.float64))
+    g = load_golden('correct_u16_dates')
+    cal = ip.CameraCalibration()
+    cal.addDarkCurrent(g['d1'], date='01 Jan 15 - 10:00')
+    cal.addDarkCurrent(g['d3'], date='01 Jan 17 - 10:00')
+    cal.addDarkCurrent(g['d2'], date='01 Jan 16 - 10:00')
+    for tag, date in (('none', None), ('mid', '01 Jun 16 - 00:00'), ('old', '01 Jan 14 - 00:00'),
+                      ('new', '01 Jan 18 - 00:00'), ('bad', 'not a date')):
+        out, _ = _quiet(cal.correct, g['raw'], threshold=0, date=date)
+        assert np.array_equal(out, g['out_' + tag]), tag
+
+
+def test_correct_error_conventions(ip):
+    cal = ip.CameraCalibration()
+    cal.addDarkCurrent(np.zeros((8, 8), np.float32))
+    with pytest.raises(Exception, match='array shapes are different'):
+        _quiet(cal.correct, np.zeros((8, 9), np.uint16))
+    with pytest.raises(NotImplementedError):
+        _quiet(cal.correct, [np.zeros((8, 8), np.uint16)] * 2)
+    out, log = _quiet(cal.correct, [np.ones((8, 8), np.uint16)], threshold=0)
+    assert np.array_equal(out, np.ones((8, 8)))
+    # a dark map of the wrong shape slipped into the store: printed, stage skipped, pipeline continues
+    cal.coeffs['dark current'][0][2] = np.zeros((3, 3), np.float32)
+    out, log = _quiet(cal.correct, np.ones((8, 8), np.uint16), threshold=0)
+    assert 'Error:' in log and np.array_equal(out, np.ones((8, 8)))
+
+
+# ---------------------------------------------------------------------------- batches
+def test_correct_batch_device_and_host(ip):
+    H, W, n = 96, 128, 7
+    g = load_golden('correct_u16_keep1')
+    cal = _cal(ip, g)
+    frames = np.stack([synth.scene(H, W, 30 + i, np.uint16) for i in range(n)])
+    single = []
+    for i in range(n):
+        o, _ = _quiet(cal.correct, frames[i], threshold=0.1)
+        single.append(o)
+    single = np.stack(single)
+    dev_out = cal.correct_batch(_dev(frames), threshold=0.1)
+    assert dev_out.dtype == torch.float32 and dev_out.is_cuda
+    assert np.array_equal(dev_out.cpu().numpy().astype(np.float64), single)
+    host_out = cal.correct_batch(frames, threshold=0.1)
+    assert host_out.dtype == np.float32 and np.array_equal(host_out.astype(np.float64), single)
+    host64 = cal.correct_batch(frames, threshold=0.1, out_dtype=np.float64)
+    assert np.array_equal(host64, single)
+    # pinned buffers + cropped output + more frames than ring slots
+    from imgprocessor_b200.engine import pinned_empty
+    pin_in = pinned_empty(frames.shape, np.uint16)
+    pin_in[...] = frames
+    l = cal.getLens(None, None)
+    l.getUndistortRectifyMap(W, H)
+    x, y, w, h = (int(v) for v in l.roi)
+    pin_out = pinned_empty((n, h, w), np.float32)
+    r = cal.correct_batch(pin_in, threshold=0.1, keep_size=False, out=pin_out)
+    assert r is pin_out and np.array_equal(pin_out.astype(np.float64), single[:, y:y + h, x:x + w])
+
+
+# ---------------------------------------------------------------------------- BASELINE.json sizes
+def test_config1_1024_f32_full_chain(ip):
+    """configs[0]: one 1024x1024 float32 frame, dark + flat + 3x3 + 5-coefficient lens, vs the float64
+    reference path (refpath == unmodified reference, pinned by test_oracle_golden)."""
+    H = W = 1024
+    raw = synth.scene(H, W, 0, np.float32)
+    dark, flat = synth.dark_map(H, W), synth.flat_map(H, W)
+    p = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    cal = ip.CameraCalibration()
+    cal.addDarkCurrent(dark)
+    cal.addFlatField(flat)
+    l = ip.LensDistortion({})
+    l.setCameraParams(*p)
+    l._coeffs['shape'] = (H, W)
+    cal.addLens(l)
+    out, _ = _quiet(cal.correct, raw, threshold=0.1)
+    ref = refpath.correct(raw, dark, flat, (K, d), 0.1)
+    assert np.abs(out - ref).max() / 4095.0 < 1e-5
+    mapx, mapy, P, roi = refpath.undistort_rectify_map(K, d, W, H)
+    want, mask = models.correct_chain_f32(raw, dark, flat, 0.1, 3, mapxy=(mapx, mapy))   # cv2's own maps
+    assert (out != want).sum() == 0
+
+
+@pytest.mark.parametrize('variant', [1, 2])
+def test_config2_4096x3000_u16_k1(ip, variant):
+    """configs[1]: a 4096x3000 uint16 frame through K1, bit-exact against the oracle at full size."""
+    H, W = 3000, 4096
+    raw, dark, flat = synth.scene(H, W, 1, np.uint16), synth.dark_map(H, W), synth.flat_map(H, W)
+    e = _eng(ip, H, W, variant)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    out, mask = e.pointwise_median(_dev(raw), 0.1, 3, want_mask=True)
+    x = models.pointwise_model(raw, dark, flat, True)
+    want, wmask = models.median_threshold_model(x, 0.1, 3)
+    assert np.array_equal(out.cpu().numpy(), want)
+    assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    assert 0.001 < wmask.mean() < 0.05
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
+def test_config3_chain_full_size_properties(ip):
+    """configs[2] frame size: full chain on a few 4096x3000 frames; frame independence (batch == single),
+    remap against cv2's own maps at full size, linearity of the border (no lens -> identity)."""
+    H, W, n = 3000, 4096, 3
+    dark, flat = synth.dark_map(H, W), synth.flat_map(H, W)
+    p = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    mapx, mapy, P, roi = refpath.undistort_rectify_map(K, d, W, H)
+    e = _eng(ip, H, W, 0)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    e.set_lens(K, d, P)
+    frames = torch.stack([_dev(synth.scene(H, W, 100 + i, np.uint16)) for i in range(n)])
+    out = e.correct_batch(frames, 0.1, 3)
+    one = e.correct_batch(frames[1], 0.1, 3)
+    assert torch.equal(out[1], one)
+    raw1 = frames[1].cpu().numpy()
+    want, _ = models.correct_chain_f32(raw1, dark, flat, 0.1, 3, mapxy=(mapx, mapy))
+    assert np.array_equal(one.cpu().numpy(), want)
+
+
+def test_config4_f32_5x5_strong_lens(ip):
+    """configs[3] at 2048x2048 (the oracle's 5x5 partition at 8192^2 needs ~7 GB): float32 frame, direct
+    medianThreshold(size=5) then LensDistortion.correct with the strong lens."""
+    H = W = 2048
+    raw = synth.scene(H, W, 2, np.float32)
+    med, ind = ip.medianThreshold(raw, 0.1, 5)
+    want, wmask = models.median_threshold_model(raw, 0.1, 5)
+    assert np.array_equal(med, want) and np.array_equal(ind, wmask)
+    p = synth.lens_strong(H, W)
+    l = ip.LensDistortion({})
+    l.setCameraParams(*p)
+    out = l.correct(med, keepSize=True)
+    ref = refpath.lens_correct(want, synth.camera_matrix(p), synth.dist_coeffs(p), keep_size=True)
+    assert (out != ref).mean() < 1e-6          # analytic map vs cv2's: at most a stray 1/32-px flip
+    assert np.abs(out - ref).max() / 4095.0 < 1e-3
