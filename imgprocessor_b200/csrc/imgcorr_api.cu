@@ -49,7 +49,8 @@ struct imgcorr_ctx {
     double exposure = 0.0, maxval = 65535.0;
     bool has_lens = false;
     LensConst lens{};
-    int k1_variant = 0, k2_variant = 0, host_slots = 4;
+    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0;
+    bool dark_finite = true, flat_finite = true;
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
     // host pipeline
@@ -141,11 +142,15 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
     if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
     switch (key) {
         case IMGCORR_OPT_K1_VARIANT:
-            if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
+            if (value < 0 || value > 3) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
             c->k1_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
             c->k2_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_K1_SEG_ROWS:
+            if (value < 0) return fail(IMGCORR_ERR_INVALID, "seg rows %d", value);
+            c->k1_seg_rows = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_HOST_SLOTS:
             if (value < 2 || value > 64) return fail(IMGCORR_ERR_INVALID, "host slots %d not in [2,64]", value);
@@ -162,14 +167,29 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
 
 extern "C" IMGCORR_API long long imgcorr_launch_count(const imgcorr_ctx* c) { return c ? c->launches : 0; }
 
-static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_device) {
-    const size_t bytes = (size_t)c->H * c->W * sizeof(float);
+static bool all_finite(const float* p, size_t n) {
+    // |x| <= FLT_MAX fails for NaN and inf; accumulate without branches
+    bool ok = true;
+    for (size_t i = 0; i < n; ++i) ok &= (fabsf(p[i]) <= 3.402823466e+38f);
+    return ok;
+}
+
+static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_device, bool* finite) {
+    const size_t n = (size_t)c->H * c->W, bytes = n * sizeof(float);
+    *finite = true;
     if (!src) {
         if (*slot) { CK(cudaDeviceSynchronize()); CK(cudaFree(*slot)); *slot = nullptr; }
         return IMGCORR_OK;
     }
     if (!*slot) CK(cudaMalloc((void**)slot, bytes));
     CK(cudaMemcpy(*slot, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    if (on_device) {
+        std::vector<float> tmp(n);
+        CK(cudaMemcpy(tmp.data(), *slot, bytes, cudaMemcpyDeviceToHost));
+        *finite = all_finite(tmp.data(), n);
+    } else {
+        *finite = all_finite(src, n);
+    }
     return IMGCORR_OK;
 }
 
@@ -179,9 +199,10 @@ extern "C" IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* c, const float* dark, c
     if (!dark && ascent) return fail(IMGCORR_ERR_INVALID, "ascent given without offset map");
     if (ascent && (depth_bits < 1 || depth_bits > 62)) return fail(IMGCORR_ERR_INVALID, "depth_bits %d", depth_bits);
     if (ascent && !(exposure_time == exposure_time)) return fail(IMGCORR_ERR_INVALID, "exposure_time is NaN");
-    int r = upload_map(c, &c->dark, dark, on_device);
+    bool fin2 = true;
+    int r = upload_map(c, &c->dark, dark, on_device, &c->dark_finite);
     if (r) return r;
-    r = upload_map(c, &c->ascent, ascent, on_device);
+    r = upload_map(c, &c->ascent, ascent, on_device, &fin2);
     if (r) return r;
     c->exposure = exposure_time;
     c->maxval = ascent ? ldexp(1.0, depth_bits) - 1.0 : 65535.0;
@@ -190,7 +211,7 @@ extern "C" IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* c, const float* dark, c
 
 extern "C" IMGCORR_API int imgcorr_set_flat(imgcorr_ctx* c, const float* flat, int on_device) {
     GUARD(c);
-    return upload_map(c, &c->flat, flat, on_device);
+    return upload_map(c, &c->flat, flat, on_device, &c->flat_finite);
 }
 
 extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], const double dist[5], const double P[9]) {
@@ -225,6 +246,7 @@ static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, void* out, uint8_
     if ((flags & IMGCORR_DO_FLAT) && c->flat) { f |= FLAG_FLAT; a.flat = c->flat; }
     if (flags & IMGCORR_DO_NAN_TO_NUM) f |= FLAG_NAN_TO_NUM;
     a.pw.flags = f; a.pw.exposure_time = c->exposure; a.pw.max_value = c->maxval;
+    a.maps_finite = ((!a.dark || c->dark_finite) && (!a.flat || c->flat_finite)) ? 1 : 0;
     a.pred = make_predicate(thr, cond == IMGCORR_COND_LT ? COND_LT : COND_GT);
     return IMGCORR_OK;
 }
@@ -237,11 +259,11 @@ extern "C" IMGCORR_API int imgcorr_pointwise_median(imgcorr_ctx* c, const void* 
     int r = fill_k1(c, a, raw_dev, out_dev, mask_dev, n_frames, threshold, ksize, cond, flags);
     if (r) return r;
     int l = 0;
-    cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, (cudaStream_t)stream, &l);
+    cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, c->k1_seg_rows, (cudaStream_t)stream, &l);
     c->launches += l;
     if (e == cudaErrorInvalidValue && l == 0)
         return fail(IMGCORR_ERR_INVALID, "unsupported dtype pair raw=%d out=%d", raw_dtype, out_dtype);
-    if (e == cudaErrorNotSupported) return fail(IMGCORR_ERR_INVALID, "TMA variant requested but shape/alignment not eligible");
+    if (e == cudaErrorNotSupported) return fail(IMGCORR_ERR_INVALID, "requested K1 variant is not eligible for this shape / dtype / alignment");
     if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
     return IMGCORR_OK;
 }
@@ -309,7 +331,7 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         int r = fill_k1(c, a, raw, out, nullptr, n, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
-        cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, st, &l);
+        cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, c->k1_seg_rows, st, &l);
         c->launches += l;
         if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
         return IMGCORR_OK;
@@ -323,7 +345,7 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         int r = fill_k1(c, a, (const char*)raw + f * raw_stride, mid, nullptr, 1, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
-        cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, st, &l);
+        cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, c->k1_seg_rows, st, &l);
         c->launches += l;
         if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
         r = run_k2(c, mid, DT_F32, (char*)out + f * out_stride, out_dtype, 1, nullptr, nullptr, border, x0, y0, ow, oh, st);

@@ -21,14 +21,18 @@ struct K1Args {
     uint8_t* mask;          // [n_frames][H][W] or null
     int H, W, n_frames;
     int ksize;              // 0 (pointwise only), 3, 5
+    int maps_finite;        // dark / flat hold no NaN / inf (checked once at upload)
     PointwiseConst pw;
     PredicateConst pred;
 };
 
-// variant: 0 = pick automatically, 1 = generic (plain coalesced loads), 2 = TMA-staged
-cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count,
+// variant: 0 = pick automatically, 1 = generic tiles (plain coalesced loads), 2 = TMA-staged tiles,
+//          3 = TMA streaming pipeline (3x3 only).  seg_rows: rows per work unit of the streaming kernel (0 = default)
+cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count, int seg_rows,
                       cudaStream_t stream, int* launches);
 bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype);
+bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype);
+cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 
 // K2: undistortion remap ---------------------------------------------------------------------
 struct K2Args {

@@ -1,0 +1,348 @@
+// K1, streaming variant (3x3): the fused dark / flat / nan_to_num / median-threshold kernel as a
+// warp-specialised TMA pipeline with the stencil window held in registers.
+//
+//   * work unit = (frame, 120-column strip, segment of rows).  A CTA is 4 consumer warps + 1 producer
+//     warp and walks its units top to bottom in chunks of 8 rows.
+//   * the producer warp (one elected lane) fills a 4-stage shared-memory ring with
+//     cp.async.bulk.tensor boxes of raw / dark / flat rows (16-byte aligned, 16-byte multiple wide,
+//     out-of-frame parts zero-filled by TMA), signalled through `full` mbarriers; consumers hand a
+//     stage back through `empty` mbarriers.  There is no CTA-wide barrier in the steady state.
+//   * each consumer lane owns one image column of its warp's 30-column slice (+1 halo lane on each
+//     side; the halo / out-of-frame lanes read the mirrored column, which is scipy's 'reflect').
+//     Per row it reads raw, dark, flat from shared memory, computes the pointwise value in float64
+//     registers (one rounding to float32), fetches the left / right neighbours with two warp shuffles,
+//     sorts the horizontal triple and combines it with the two previous rows' triples (kept in
+//     registers) into the median of 9; predicate + select + one coalesced store per row.
+//   * vertical 'reflect' needs no halo rows: the first / last row's sorted triple is used twice.
+//
+// Same arithmetic as the tile kernels (imgcorr_core.cuh) — results are bit-identical.
+#include <cuda.h>
+#include "imgcorr_kernels.cuh"
+
+namespace imgcorr {
+
+constexpr int KS_CW = 4;                    // consumer warps per CTA
+constexpr int KS_SW = 30;                   // output columns per consumer warp
+constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
+constexpr int KS_R = 8;                     // rows per pipeline stage
+constexpr int KS_NSTAGE = 4;
+constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
+constexpr int KS_MAPX = 4;
+constexpr int KS_THREADS = (KS_CW + 1) * 32;
+
+template <typename RawT> struct StreamBox {
+    static constexpr int XOFF = 16 / (int)sizeof(RawT);                        // u8 16, u16 8, f32 4
+    static constexpr int GRAN = 16 / (int)sizeof(RawT);
+    // the box starts at the 16-byte boundary at or left of tx0, minus XOFF: columns tx0-1 .. tx0+120 are inside
+    static constexpr int BOXW = ((KS_TW + 2 * XOFF + GRAN - 1) / GRAN) * GRAN;  // u8 160, u16 136, f32 128
+    static constexpr size_t raw_bytes = (size_t)KS_R * BOXW * sizeof(RawT);     // multiples of 128
+    static constexpr size_t map_bytes = (size_t)KS_R * KS_MAPW * sizeof(float);
+    static constexpr size_t stage_bytes = raw_bytes + 2 * map_bytes;
+    static constexpr size_t bar_off = KS_NSTAGE * stage_bytes;
+    static constexpr size_t total = bar_off + 2 * KS_NSTAGE * sizeof(uint64_t) + 64;
+};
+
+__device__ __forceinline__ uint32_t ks_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ks_bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ks_s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ks_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ks_s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ks_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ks_s32(bar)) : "memory");
+}
+__device__ __forceinline__ void ks_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(ks_s32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void ks_tma_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(ks_s32(dst)), "l"(tm), "r"(ks_s32(bar)), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void ks_tma_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(ks_s32(dst)), "l"(tm), "r"(ks_s32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+
+template <typename T> struct StreamRaw;
+template <> struct StreamRaw<uint8_t>  { static __device__ __forceinline__ void ld(uint8_t v, double& d, float& a)  { d = (double)(int)v; a = 0.0f; } };
+template <> struct StreamRaw<uint16_t> { static __device__ __forceinline__ void ld(uint16_t v, double& d, float& a) { d = (double)(int)v; a = 0.0f; } };
+template <> struct StreamRaw<float>    { static __device__ __forceinline__ void ld(float v, double& d, float& a)    { d = (double)v; a = fabsf(v); } };
+
+template <typename OutT> __device__ __forceinline__ OutT ks_out(float v);
+template <> __device__ __forceinline__ float    ks_out<float>(float v)    { return v; }
+template <> __device__ __forceinline__ uint16_t ks_out<uint16_t>(float v) { return sat_u16(v); }
+template <> __device__ __forceinline__ uint8_t  ks_out<uint8_t>(float v)  { return sat_u8(v); }
+
+struct UnitGeom {
+    int frame, tx0, ys, ye, yl0, n_in, nchunk;
+};
+__device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int seg_rows, int H) {
+    UnitGeom u;
+    const int strip = unit % strips;
+    int t = unit / strips;
+    const int seg = t % segs;
+    u.frame = t / segs;
+    u.tx0 = strip * KS_TW;
+    u.ys = seg * seg_rows;
+    u.ye = u.ys + seg_rows < H ? u.ys + seg_rows : H;
+    u.yl0 = u.ys > 0 ? u.ys - 1 : 0;
+    const int yl1 = u.ye < H ? u.ye : H - 1;
+    u.n_in = yl1 - u.yl0 + 1;
+    u.nchunk = (u.n_in + KS_R - 1) / KS_R;
+    return u;
+}
+
+// CFG >= 0 bakes the per-launch switches into the instruction stream (the kernel is issue bound: every
+// per-row flag test costs); CFG < 0 reads them from the arguments.
+enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32 };
+// KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
+
+template <typename RawT, typename OutT, int CFG>
+__global__ void __launch_bounds__(KS_THREADS)
+k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_dark,
+                 const __grid_constant__ CUtensorMap tm_flat, K1Args a, int strips, int segs, int seg_rows, int total_units) {
+    using B = StreamBox<RawT>;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = (uint64_t*)(smem + B::bar_off);
+    uint64_t* empty = full + KS_NSTAGE;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool has_dark = CFG >= 0 ? (CFG & KS_DARK) != 0 : a.dark != nullptr;
+    const bool has_flat = CFG >= 0 ? (CFG & KS_FLAT) != 0 : a.flat != nullptr;
+    const bool has_mask = CFG >= 0 ? (CFG & KS_MASK) != 0 : a.mask != nullptr;
+    const bool check = CFG >= 0 ? (CFG & KS_CHECK) != 0 : true;
+    const int flags = CFG >= 0 ? ((CFG & KS_DARK ? FLAG_DARK : 0) | (CFG & KS_FLAT ? FLAG_FLAT : 0) | (CFG & KS_N2N ? FLAG_NAN_TO_NUM : 0))
+                               : a.pw.flags;
+    const int H = a.H, W = a.W;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < KS_NSTAGE; ++s) { ks_bar_init(&full[s], 1); ks_bar_init(&empty[s], KS_CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == KS_CW) {
+        // ------------------------------------------------------------------ producer
+        if (lane != 0) return;
+        const uint32_t tx_bytes = (uint32_t)(B::raw_bytes + (has_dark ? B::map_bytes : 0) + (has_flat ? B::map_bytes : 0));
+        uint32_t g = 0;
+        for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+            const UnitGeom u = ks_unit(unit, strips, segs, seg_rows, H);
+            for (int k = 0; k < u.nchunk; ++k, ++g) {
+                const int stage = g % KS_NSTAGE;
+                ks_wait(&empty[stage], ((g / KS_NSTAGE) & 1) ^ 1);
+                uint8_t* base = smem + (size_t)stage * B::stage_bytes;
+                const int y = u.yl0 + k * KS_R;
+                ks_expect_tx(&full[stage], tx_bytes);
+                ks_tma_3d(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame);
+                if (has_dark) ks_tma_2d(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
+                if (has_flat) ks_tma_2d(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const PointwiseConst pw = a.pw;
+    PredicateConst pred = a.pred;
+    if (CFG >= 0) pred.cond = (CFG & KS_LT) ? COND_LT : COND_GT;
+    const int lc = warp * KS_SW - 1 + lane;            // strip-local column of this lane: -1 .. 120
+    uint32_t g = 0;
+
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const UnitGeom u = ks_unit(unit, strips, segs, seg_rows, H);
+        const int gc = u.tx0 + lc;
+        const int rc = reflect_index(gc, W);             // scipy 'reflect' in x: halo / outside lanes read the mirrored column
+        int mcol = rc - (u.tx0 - KS_MAPX);
+        mcol = mcol < 0 ? 0 : (mcol > KS_MAPW - 1 ? KS_MAPW - 1 : mcol);
+        int rcol = rc - ((u.tx0 / B::GRAN) * B::GRAN - B::XOFF);
+        rcol = rcol < 0 ? 0 : (rcol > B::BOXW - 1 ? B::BOXW - 1 : rcol);
+        const bool valid = lane >= 1 && lane <= KS_SW && gc < W;
+        const int i_first = u.ys == 0 ? 1 : 2;           // first input row index whose step emits an output row
+        const ptrdiff_t o0 = ((ptrdiff_t)u.frame * H + u.yl0 - 1) * W + gc;          // row (yl0 + i - 1) at step i
+        OutT* outp = (OutT*)a.out + o0;
+        uint8_t* maskp = has_mask ? a.mask + o0 : nullptr;
+
+        Sorted3<float> s0, s1;
+        float c1;
+        int i = 0;
+
+        auto pixel = [&](const uint8_t* base, int j) -> float {
+            const RawT rv = ((const RawT*)base)[j * B::BOXW + rcol];
+            const float d = has_dark ? ((const float*)(base + B::raw_bytes))[j * KS_MAPW + mcol] : 0.0f;
+            const float f = has_flat ? ((const float*)(base + B::raw_bytes + B::map_bytes))[j * KS_MAPW + mcol] : 0.0f;
+            double rd; float ra;
+            StreamRaw<RawT>::ld(rv, rd, ra);
+            bool ok;
+            float x = pointwise_fast(flags, rd, ra, d, f, ok);
+            if (check) { if (!ok) x = pointwise<float>(pw, rd, d, 0.0f, f); }
+            return x;
+        };
+        auto emit = [&](const Sorted3<float>& t2, bool on) {
+            const float med = median9(s0, s1, t2);
+            bool rep;
+            if (!predicate_certain(c1, med, pred, rep)) rep = predicate_exact((double)c1, (double)med, pred);
+            if (on) {
+                *outp = ks_out<OutT>(rep ? med : c1);
+                if (has_mask) *maskp = rep ? 1 : 0;
+            }
+        };
+        auto row = [&](const uint8_t* base, int j) {
+            const float x = pixel(base, j);
+            const float l = __shfl_up_sync(0xffffffffu, x, 1);
+            const float r = __shfl_down_sync(0xffffffffu, x, 1);
+            const Sorted3<float> t2 = sort3(l, x, r);
+            emit(t2, valid && i >= i_first);
+            s0 = s1; s1 = t2; c1 = x;
+            outp += W;
+            if (has_mask) maskp += W;
+            ++i;
+        };
+
+        for (int k = 0; k < u.nchunk; ++k, ++g) {
+            const int stage = g % KS_NSTAGE;
+            ks_wait(&full[stage], (g / KS_NSTAGE) & 1);
+            const uint8_t* base = smem + (size_t)stage * B::stage_bytes;
+            if (k == 0) {
+                // vertical 'reflect' at the top (and a defined s0/s1 elsewhere): the first row's triple is used twice
+                const float x = pixel(base, 0);
+                const float l = __shfl_up_sync(0xffffffffu, x, 1);
+                const float r = __shfl_down_sync(0xffffffffu, x, 1);
+                s1 = sort3(l, x, r);
+                s0 = s1;
+                c1 = x;
+            }
+            const int rows = u.n_in - k * KS_R;
+            if (rows >= KS_R) {
+#pragma unroll
+                for (int j = 0; j < KS_R; ++j) row(base, j);
+            } else {
+                for (int j = 0; j < rows; ++j) row(base, j);
+            }
+            __syncwarp();
+            if (lane == 0) ks_arrive(&empty[stage]);
+        }
+        if (u.ye == H) {
+            // vertical 'reflect' at the bottom: output row H-1 sees (H-2, H-1, H-1)
+            const Sorted3<float> t2 = s1;
+            emit(t2, valid);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled_s)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled_s ks_encode_fn() {
+    static PFN_encodeTiled_s fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled_s)p;
+    }
+    return fn;
+}
+
+static bool ks_make_map(CUtensorMap* tm, CUtensorMapDataType dt, size_t esz, const void* ptr, int W, int H, int N,
+                        int boxw, int boxh) {
+    PFN_encodeTiled_s enc = ks_encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(N > 0 ? N : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)W * esz, (cuuint64_t)W * H * esz};
+    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    const int rank = N > 0 ? 3 : 2;
+    return enc(tm, dt, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
+    if (a.ksize != 3) return false;
+    if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
+    if (out_dtype != DT_F32 && !(raw_dtype == DT_U16 && out_dtype == DT_U16) && !(raw_dtype == DT_U8 && out_dtype == DT_U8)) return false;
+    if (a.pw.flags & FLAG_DARK_LINEAR) return false;
+    const size_t esz = dtype_size(raw_dtype);
+    if (((size_t)a.W * esz) % 16 || ((size_t)a.W * 4) % 16) return false;
+    if (((size_t)a.H * a.W * esz) % 16) return false;
+    if (((uintptr_t)a.raw) % 16) return false;
+    if (a.dark && ((uintptr_t)a.dark) % 16) return false;
+    if (a.flat && ((uintptr_t)a.flat) % 16) return false;
+    return ks_encode_fn() != nullptr;
+}
+
+template <typename RawT, typename OutT>
+static cudaError_t launch_stream_t(const K1Args& a, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
+    using B = StreamBox<RawT>;
+    CUtensorMap tr, td, tf;
+    if (!ks_make_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
+    if (!ks_make_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.dark)
+        return cudaErrorInvalidValue;
+    if (!ks_make_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
+        return cudaErrorInvalidValue;
+    // pick the instantiation: the two hot configurations are fully specialised, the rest read their flags at run time
+    const bool check = !a.maps_finite || sizeof(RawT) == 4;
+    const int f = a.pw.flags;
+    const bool chain = a.dark && a.flat && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
+                       a.pred.cond == COND_GT;
+    const bool plain = !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
+    int slot;
+    if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N>; slot = 0; }
+    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_CHECK>; slot = 1; }
+    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK>; slot = 2; }
+    else { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 3; }
+    static int per_sm[4] = {0, 0, 0, 0};
+    if (!per_sm[slot]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
+        if (e != cudaSuccess) return e;
+        int n = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, KS_THREADS, B::total);
+        per_sm[slot] = n < 1 ? 1 : n;
+    }
+    const int strips = (a.W + KS_TW - 1) / KS_TW;
+    if (seg_rows <= 0) seg_rows = 64;
+    if (seg_rows < 4) seg_rows = 4;
+    const int segs = (a.H + seg_rows - 1) / seg_rows;
+    const long long total = (long long)strips * segs * a.n_frames;
+    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+    long long grid = (long long)sm_count * per_sm[slot];
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, KS_THREADS, B::total, st>>>(tr, td, tf, a, strips, segs, seg_rows, (int)total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t st) {
+    switch (raw_dtype) {
+        case DT_U8:
+            if (out_dtype == DT_F32) return launch_stream_t<uint8_t, float>(a, CU_TENSOR_MAP_DATA_TYPE_UINT8, sm_count, seg_rows, st);
+            if (out_dtype == DT_U8) return launch_stream_t<uint8_t, uint8_t>(a, CU_TENSOR_MAP_DATA_TYPE_UINT8, sm_count, seg_rows, st);
+            break;
+        case DT_U16:
+            if (out_dtype == DT_F32) return launch_stream_t<uint16_t, float>(a, CU_TENSOR_MAP_DATA_TYPE_UINT16, sm_count, seg_rows, st);
+            if (out_dtype == DT_U16) return launch_stream_t<uint16_t, uint16_t>(a, CU_TENSOR_MAP_DATA_TYPE_UINT16, sm_count, seg_rows, st);
+            break;
+        case DT_F32:
+            if (out_dtype == DT_F32) return launch_stream_t<float, float>(a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sm_count, seg_rows, st);
+            break;
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace imgcorr

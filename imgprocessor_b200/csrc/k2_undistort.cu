@@ -10,6 +10,10 @@
 // The same kernel also serves explicit float32 maps (distortImage, parity tests against
 // cv2's own maps).  When n_frames > 1 the coordinates and weights of a pixel are computed once
 // and applied to every frame of the launch.
+//
+// A thread owns one output column and four rows of a 32x32 tile (consecutive lanes = consecutive
+// columns: coalesced stores, neighbouring gathers).  When P^-1 has no cross terms (what
+// getOptimalNewCameraMatrix always produces) x depends on the column only and is hoisted.
 #include "imgcorr_kernels.cuh"
 
 namespace imgcorr {
@@ -68,7 +72,8 @@ __device__ __forceinline__ DstT remap_pixel(const SrcT* __restrict__ src, int H,
     return Blend<SrcT, DstT>::run(v00, v01, v10, v11, c);
 }
 
-template <typename SrcT, typename DstT, bool ANALYTIC>
+// MODE: 0 explicit maps, 1 analytic general P, 2 analytic separable P^-1 (x = x(u), y = y(v))
+template <typename SrcT, typename DstT, int MODE>
 __global__ void __launch_bounds__(K2_BX * K2_BY) k2_remap_kernel(K2Args a) {
     const int ox = blockIdx.x * K2_BX + (threadIdx.x % K2_BX);
     const int ty = threadIdx.x / K2_BX;
@@ -76,23 +81,33 @@ __global__ void __launch_bounds__(K2_BX * K2_BY) k2_remap_kernel(K2Args a) {
     const int u = ox + a.x0;
     const SrcT bval = border_cast<SrcT>(a.border);
     const size_t src_stride = (size_t)a.H * a.W, dst_stride = (size_t)a.oh * a.ow;
+    const int H = a.H, W = a.W, nf = a.n_frames;
+    const LensConst L = a.lens;
+    double xc = 0.0, xc2 = 0.0;
+    if (MODE == 2) {
+        xc = fma((double)u, L.ir[0], L.ir[2]);
+        xc2 = dmul(xc, xc);
+    }
 #pragma unroll
     for (int j = 0; j < K2_ROWS; ++j) {
         const int oy = blockIdx.y * (K2_BY * K2_ROWS) + ty + j * K2_BY;
         if (oy >= a.oh) break;
         const int v = oy + a.y0;
         float mx, my;
-        if (ANALYTIC) {
-            undistort_map(a.lens, u, v, mx, my);
+        if (MODE == 2) {
+            const double y = fma((double)v, L.ir[4], L.ir[5]);
+            map_distort(L, xc, y, xc2, dmul(y, y), mx, my);
+        } else if (MODE == 1) {
+            undistort_map(L, u, v, mx, my);
         } else {
-            mx = __ldg(a.mapx + (size_t)v * a.W + u);
-            my = __ldg(a.mapy + (size_t)v * a.W + u);
+            mx = __ldg(a.mapx + (size_t)v * W + u);
+            my = __ldg(a.mapy + (size_t)v * W + u);
         }
         const FixedCoord c = fixed_coord(mx, my);
         const SrcT* src = (const SrcT*)a.src;
         DstT* dst = (DstT*)a.dst + (size_t)oy * a.ow + ox;
-        for (int f = 0; f < a.n_frames; ++f) {
-            *dst = remap_pixel<SrcT, DstT>(src, a.H, a.W, c, bval);
+        for (int f = 0; f < nf; ++f) {
+            *dst = remap_pixel<SrcT, DstT>(src, H, W, c, bval);
             src += src_stride;
             dst += dst_stride;
         }
@@ -109,17 +124,21 @@ __global__ void __launch_bounds__(256) k2_write_maps_kernel(LensConst lens, floa
     mapy[(size_t)v * W + u] = my;
 }
 
+static bool separable(const LensConst& L) { return L.affine && L.ir[1] == 0.0 && L.ir[3] == 0.0; }
+
 template <typename SrcT, typename DstT>
 static cudaError_t launch_t(const K2Args& a, cudaStream_t st) {
     dim3 grid((a.ow + K2_BX - 1) / K2_BX, (a.oh + K2_BY * K2_ROWS - 1) / (K2_BY * K2_ROWS));
-    if (a.mapx) k2_remap_kernel<SrcT, DstT, false><<<grid, K2_BX * K2_BY, 0, st>>>(a);
-    else k2_remap_kernel<SrcT, DstT, true><<<grid, K2_BX * K2_BY, 0, st>>>(a);
+    if (a.mapx) k2_remap_kernel<SrcT, DstT, 0><<<grid, K2_BX * K2_BY, 0, st>>>(a);
+    else if (separable(a.lens)) k2_remap_kernel<SrcT, DstT, 2><<<grid, K2_BX * K2_BY, 0, st>>>(a);
+    else k2_remap_kernel<SrcT, DstT, 1><<<grid, K2_BX * K2_BY, 0, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t st, int* launches) {
     (void)variant;
     if (a.n_frames <= 0 || a.ow <= 0 || a.oh <= 0) return cudaSuccess;
+    if (a.H > 32767 || a.W > 32767) return cudaErrorInvalidValue;      // OpenCV's remap itself is limited to short coordinates
     if (a.x0 < 0 || a.y0 < 0 || a.x0 + a.ow > a.W || a.y0 + a.oh > a.H) return cudaErrorInvalidValue;
     if ((a.mapx == nullptr) != (a.mapy == nullptr)) return cudaErrorInvalidValue;
     if (launches) ++*launches;
