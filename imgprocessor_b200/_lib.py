@@ -10,7 +10,7 @@ _LIB = None
 U8, U16, F32, F64 = 0, 1, 2, 3
 COND_GT, COND_LT = 0, 1
 DO_DARK, DO_FLAT, DO_NAN_TO_NUM = 1, 2, 4
-OPT_K1_VARIANT, OPT_K2_VARIANT, OPT_HOST_SLOTS, OPT_K1_SEG_ROWS = 1, 2, 3, 4
+OPT_K1_VARIANT, OPT_K2_VARIANT, OPT_HOST_SLOTS, OPT_K1_SEG_ROWS, OPT_PROFILE, OPT_CHAIN_GROUP = 1, 2, 3, 4, 5, 6
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
 
 c_void_p, c_int, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
@@ -24,6 +24,7 @@ SIGNATURES = {
     'imgcorr_ctx_destroy': (c_int, [c_void_p]),
     'imgcorr_set_option': (c_int, [c_void_p, c_int, c_int]),
     'imgcorr_launch_count': (ctypes.c_longlong, [c_void_p]),
+    'imgcorr_profile_read': (c_int, [c_void_p, ctypes.POINTER(c_double)]),
     'imgcorr_set_dark': (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_int, c_int]),
     'imgcorr_set_flat': (c_int, [c_void_p, c_void_p, c_int]),
     'imgcorr_set_lens': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),

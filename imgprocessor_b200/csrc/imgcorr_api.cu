@@ -49,7 +49,11 @@ struct imgcorr_ctx {
     double exposure = 0.0, maxval = 65535.0;
     bool has_lens = false;
     LensConst lens{};
-    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0;
+    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 1;
+    long long chain_groups_seen = 0;
+    double prof_frames[2] = {0.0, 0.0};
+    std::vector<cudaEvent_t> prof_ev[2];      // [kernel] start/stop pairs
+    size_t mid_frames = 0;
     bool dark_finite = true, flat_finite = true;
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
@@ -134,6 +138,7 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->flat);
     cudaFree(c->mid[0]);
     cudaFree(c->mid[1]);
+    for (int k = 0; k < 2; ++k) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     delete c;
     return IMGCORR_OK;
 }
@@ -147,6 +152,14 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
             c->k2_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_PROFILE:
+            if (value < 0) return fail(IMGCORR_ERR_INVALID, "profile stride %d", value);
+            c->profile = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_CHAIN_GROUP:
+            if (value < 1 || value > 64) return fail(IMGCORR_ERR_INVALID, "chain group %d not in [1,64]", value);
+            c->chain_group = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K1_SEG_ROWS:
             if (value < 0) return fail(IMGCORR_ERR_INVALID, "seg rows %d", value);
@@ -166,6 +179,35 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
 }
 
 extern "C" IMGCORR_API long long imgcorr_launch_count(const imgcorr_ctx* c) { return c ? c->launches : 0; }
+
+static void prof_mark(imgcorr_ctx* c, int which, cudaStream_t st) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, st);
+    c->prof_ev[which].push_back(e);
+}
+
+extern "C" IMGCORR_API int imgcorr_profile_read(imgcorr_ctx* c, double out[4]) {
+    GUARD(c);
+    if (!out) return fail(IMGCORR_ERR_INVALID, "out is null");
+    for (int k = 0; k < 2; ++k) {
+        double ms = 0.0;
+        auto& v = c->prof_ev[k];
+        const size_t pairs = v.size() / 2;
+        for (size_t i = 0; i < pairs; ++i) {
+            float t = 0.f;
+            CK(cudaEventSynchronize(v[2 * i + 1]));
+            CK(cudaEventElapsedTime(&t, v[2 * i], v[2 * i + 1]));
+            ms += t;
+        }
+        for (auto e : v) cudaEventDestroy(e);
+        v.clear();
+        out[2 * k] = ms;
+        out[2 * k + 1] = c->prof_frames[k];
+        c->prof_frames[k] = 0.0;
+    }
+    return IMGCORR_OK;
+}
 
 static bool all_finite(const float* p, size_t n) {
     // |x| <= FLT_MAX fails for NaN and inf; accumulate without branches
@@ -336,19 +378,36 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
         return IMGCORR_OK;
     }
-    for (int i = 0; i < 2; ++i)
-        if (!c->mid[i]) CK(cudaMalloc((void**)&c->mid[i], npx * sizeof(float)));
+    // K1 -> K2 in groups of `chain_group` frames: the K1 output of a group stays in two alternating scratch
+    // buffers (L2-resident for small groups); K2 evaluates each pixel's map once per group.
+    const int grp = c->chain_group < n ? c->chain_group : (n > 0 ? n : 1);
+    if (c->mid_frames < (size_t)grp) {
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 2; ++i) {
+            if (c->mid[i]) { CK(cudaFree(c->mid[i])); c->mid[i] = nullptr; }
+            CK(cudaMalloc((void**)&c->mid[i], npx * sizeof(float) * grp));
+        }
+        c->mid_frames = grp;
+    }
     const size_t out_stride = (size_t)ow * oh * dtype_size(out_dtype);
-    for (int f = 0; f < n; ++f) {
-        float* mid = c->mid[f & 1];
+    int gi = 0;
+    for (int f = 0; f < n; f += grp, ++gi) {
+        const int nf = n - f < grp ? n - f : grp;
+        float* mid = c->mid[gi & 1];
+        const bool prof = c->profile > 0 && (c->chain_groups_seen++ % c->profile) == 0;
+        if (prof) { c->prof_frames[0] += nf; c->prof_frames[1] += nf; }
         K1Args a;
-        int r = fill_k1(c, a, (const char*)raw + f * raw_stride, mid, nullptr, 1, thr, ksize, IMGCORR_COND_GT, flags);
+        int r = fill_k1(c, a, (const char*)raw + f * raw_stride, mid, nullptr, nf, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
+        if (prof) prof_mark(c, 0, st);
         cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, c->k1_seg_rows, st, &l);
+        if (prof) prof_mark(c, 0, st);
         c->launches += l;
         if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
-        r = run_k2(c, mid, DT_F32, (char*)out + f * out_stride, out_dtype, 1, nullptr, nullptr, border, x0, y0, ow, oh, st);
+        if (prof) prof_mark(c, 1, st);
+        r = run_k2(c, mid, DT_F32, (char*)out + f * out_stride, out_dtype, nf, nullptr, nullptr, border, x0, y0, ow, oh, st);
+        if (prof) prof_mark(c, 1, st);
         if (r) return r;
     }
     return IMGCORR_OK;

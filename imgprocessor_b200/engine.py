@@ -79,6 +79,12 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.imgcorr_launch_count(self._h))
 
+    def profile_read(self):
+        """(k1_ms, k1_launches, k2_ms, k2_launches) of the event-bracketed launches since the last call"""
+        buf = (ctypes.c_double * 4)()
+        _lib.check(self.lib.imgcorr_profile_read(self._h, buf))
+        return tuple(buf)
+
     def _stream(self):
         return ctypes.c_void_p(torch().cuda.current_stream(self.device).cuda_stream)
 

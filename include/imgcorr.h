@@ -65,7 +65,10 @@ enum {
     IMGCORR_OPT_K1_VARIANT = 1, /* 0 auto, 1 generic tiles, 2 TMA-staged tiles, 3 TMA streaming pipeline (2, 3 fail if not eligible) */
     IMGCORR_OPT_K2_VARIANT = 2, /* reserved */
     IMGCORR_OPT_HOST_SLOTS = 3, /* depth of the pinned / device staging ring of the *_host calls (default 4) */
-    IMGCORR_OPT_K1_SEG_ROWS = 4 /* rows per work unit of the streaming K1 kernel (0 = default) */
+    IMGCORR_OPT_K1_SEG_ROWS = 4, /* rows per work unit of the streaming K1 kernel (0 = default) */
+    IMGCORR_OPT_PROFILE = 5,     /* n > 0: bracket the K1 and K2 launch of every n-th frame group of the chain with CUDA
+                                    events on the launching stream (read with imgcorr_profile_read); 0 = off */
+    IMGCORR_OPT_CHAIN_GROUP = 6  /* frames per K1 / K2 launch inside imgcorr_correct_batch (default 1) */
 };
 
 IMGCORR_API const char* imgcorr_last_error(void);
@@ -81,6 +84,10 @@ IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* ctx);
 IMGCORR_API int imgcorr_set_option(imgcorr_ctx* ctx, int key, int value);
 /* kernels launched by this context so far (bench.py's gpu_launches claim) */
 IMGCORR_API long long imgcorr_launch_count(const imgcorr_ctx* ctx);
+/* Sum the event-bracketed launch durations collected since the last call (IMGCORR_OPT_PROFILE):
+ * out[0] = K1 milliseconds, out[1] = frames those K1 launches processed, out[2] = K2 milliseconds, out[3] = frames.
+ * Synchronises on the recorded events. */
+IMGCORR_API int imgcorr_profile_read(imgcorr_ctx* ctx, double out[4]);
 
 /* Dark current (calcDarkCurrent, camera/CameraCalibration.py:504-518).
  *   ascent == NULL : bg = dark                                   (entry built by addDarkCurrent(arr), :516)
