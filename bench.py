@@ -89,7 +89,7 @@ class ClockSampler(object):
                         self.reasons.add(n)
             except Exception:
                 pass
-            self._stop.wait(0.02)
+            self._stop.wait(0.005)
 
     def __enter__(self):
         if self.nv is not None:

@@ -51,7 +51,7 @@ class ImgcorrError(RuntimeError):
 
 
 def lib_path():
-    return _build.LIB
+    return os.environ.get('IMGCORR_LIB') or _build.LIB      # IMGCORR_LIB: development override (kernel variants)
 
 
 def lib():

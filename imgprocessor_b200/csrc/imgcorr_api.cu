@@ -49,12 +49,15 @@ struct imgcorr_ctx {
     double exposure = 0.0, maxval = 65535.0;
     bool has_lens = false;
     LensConst lens{};
+    double* lens_dev = nullptr;
     int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 1;
     long long chain_groups_seen = 0;
     double prof_frames[2] = {0.0, 0.0};
     std::vector<cudaEvent_t> prof_ev[2];      // [kernel] start/stop pairs
     size_t mid_frames = 0;
     bool dark_finite = true, flat_finite = true;
+    float* flat_nz = nullptr;                 // flat with zeros replaced by 1.0
+    double dark_absmax = 0.0, flat_absmin = 1.0;   // over finite entries (flat: non-zero entries)
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
     // host pipeline
@@ -136,8 +139,10 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->dark);
     cudaFree(c->ascent);
     cudaFree(c->flat);
+    cudaFree(c->flat_nz);
     cudaFree(c->mid[0]);
     cudaFree(c->mid[1]);
+    cudaFree(c->lens_dev);
     for (int k = 0; k < 2; ++k) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     delete c;
     return IMGCORR_OK;
@@ -147,7 +152,7 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
     if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
     switch (key) {
         case IMGCORR_OPT_K1_VARIANT:
-            if (value < 0 || value > 3) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
+            if (value < 0 || value > 4) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
             c->k1_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
@@ -216,7 +221,8 @@ static bool all_finite(const float* p, size_t n) {
     return ok;
 }
 
-static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_device, bool* finite) {
+static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_device, bool* finite,
+                      std::vector<float>* host_copy = nullptr) {
     const size_t n = (size_t)c->H * c->W, bytes = n * sizeof(float);
     *finite = true;
     if (!src) {
@@ -225,13 +231,16 @@ static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_dev
     }
     if (!*slot) CK(cudaMalloc((void**)slot, bytes));
     CK(cudaMemcpy(*slot, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
-    if (on_device) {
-        std::vector<float> tmp(n);
-        CK(cudaMemcpy(tmp.data(), *slot, bytes, cudaMemcpyDeviceToHost));
-        *finite = all_finite(tmp.data(), n);
-    } else {
-        *finite = all_finite(src, n);
+    std::vector<float> tmp;
+    const float* h = src;
+    if (on_device || host_copy) {
+        std::vector<float>& dst = host_copy ? *host_copy : tmp;
+        dst.resize(n);
+        if (on_device) CK(cudaMemcpy(dst.data(), *slot, bytes, cudaMemcpyDeviceToHost));
+        else memcpy(dst.data(), src, bytes);
+        h = dst.data();
     }
+    *finite = all_finite(h, n);
     return IMGCORR_OK;
 }
 
@@ -242,8 +251,11 @@ extern "C" IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* c, const float* dark, c
     if (ascent && (depth_bits < 1 || depth_bits > 62)) return fail(IMGCORR_ERR_INVALID, "depth_bits %d", depth_bits);
     if (ascent && !(exposure_time == exposure_time)) return fail(IMGCORR_ERR_INVALID, "exposure_time is NaN");
     bool fin2 = true;
-    int r = upload_map(c, &c->dark, dark, on_device, &c->dark_finite);
+    std::vector<float> h;
+    int r = upload_map(c, &c->dark, dark, on_device, &c->dark_finite, &h);
     if (r) return r;
+    c->dark_absmax = 0.0;
+    for (float v : h) { const float av = fabsf(v); if (av <= 3.402823466e+38f && av > c->dark_absmax) c->dark_absmax = av; }
     r = upload_map(c, &c->ascent, ascent, on_device, &fin2);
     if (r) return r;
     c->exposure = exposure_time;
@@ -253,7 +265,24 @@ extern "C" IMGCORR_API int imgcorr_set_dark(imgcorr_ctx* c, const float* dark, c
 
 extern "C" IMGCORR_API int imgcorr_set_flat(imgcorr_ctx* c, const float* flat, int on_device) {
     GUARD(c);
-    return upload_map(c, &c->flat, flat, on_device, &c->flat_finite);
+    std::vector<float> h;
+    int r = upload_map(c, &c->flat, flat, on_device, &c->flat_finite, &h);
+    if (r) return r;
+    if (!flat) {
+        if (c->flat_nz) { CK(cudaFree(c->flat_nz)); c->flat_nz = nullptr; }
+        return IMGCORR_OK;
+    }
+    // zero-free copy for the streaming kernel + the smallest non-zero magnitude (overflow proof)
+    double mn = 3.5e38;
+    for (float& v : h) {
+        if (v == 0.0f) v = 1.0f;
+        const float av = fabsf(v);
+        if (av <= 3.402823466e+38f && av < mn) mn = av;
+    }
+    c->flat_absmin = mn;
+    if (!c->flat_nz) CK(cudaMalloc((void**)&c->flat_nz, h.size() * sizeof(float)));
+    CK(cudaMemcpy(c->flat_nz, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return IMGCORR_OK;
 }
 
 extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], const double dist[5], const double P[9]) {
@@ -263,15 +292,26 @@ extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], c
     LensConst L{};
     if (!invert3x3(P, L.ir)) return fail(IMGCORR_ERR_INVALID, "new camera matrix P is singular");
     L.k1 = dist[0]; L.k2 = dist[1]; L.p1 = dist[2]; L.p2 = dist[3]; L.k3 = dist[4];
+    L.p1x2 = L.p1 + L.p1; L.p2x2 = L.p2 + L.p2;
     L.fx = K[0]; L.fy = K[4]; L.cx = K[2]; L.cy = K[5];
     L.affine = (L.ir[6] == 0.0 && L.ir[7] == 0.0 && L.ir[8] == 1.0) ? 1 : 0;
+    double pack[LP_COUNT] = {0};
+    pack[LP_K1] = L.k1; pack[LP_K2] = L.k2; pack[LP_K3] = L.k3; pack[LP_P1] = L.p1; pack[LP_P2] = L.p2;
+    pack[LP_P1X2] = L.p1x2; pack[LP_P2X2] = L.p2x2; pack[LP_FX] = L.fx; pack[LP_FY] = L.fy; pack[LP_CX] = L.cx;
+    pack[LP_CY] = L.cy; pack[LP_IR0] = L.ir[0]; pack[LP_IR2] = L.ir[2]; pack[LP_IR4] = L.ir[4]; pack[LP_IR5] = L.ir[5];
+    {
+        DeviceGuard g(c->device);
+        if (!g.ok) return cuda_fail(cudaGetLastError(), "cudaSetDevice");
+        if (!c->lens_dev) CK(cudaMalloc((void**)&c->lens_dev, sizeof pack));
+        CK(cudaMemcpy(c->lens_dev, pack, sizeof pack, cudaMemcpyHostToDevice));
+    }
     c->lens = L;
     c->has_lens = true;
     return IMGCORR_OK;
 }
 
-static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, void* out, uint8_t* mask, int n, double thr, int ksize,
-                   int cond, int flags) {
+static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, int raw_dtype, void* out, uint8_t* mask, int n, double thr,
+                   int ksize, int cond, int flags) {
     if (!raw || !out) return fail(IMGCORR_ERR_INVALID, "null image pointer");
     if (n < 0) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n);
     if (!(thr > 0.0)) ksize = 0;                      // also NaN
@@ -289,6 +329,14 @@ static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, void* out, uint8_
     if (flags & IMGCORR_DO_NAN_TO_NUM) f |= FLAG_NAN_TO_NUM;
     a.pw.flags = f; a.pw.exposure_time = c->exposure; a.pw.max_value = c->maxval;
     a.maps_finite = ((!a.dark || c->dark_finite) && (!a.flat || c->flat_finite)) ? 1 : 0;
+    a.flat_nz = a.flat ? c->flat_nz : nullptr;
+    // integer frames: |raw - dark| <= raw_max + max|dark|; divided by min|flat| it must stay below FLT_MAX
+    a.no_overflow = 0;
+    if (a.maps_finite && (raw_dtype == DT_U8 || raw_dtype == DT_U16)) {
+        const double num = (raw_dtype == DT_U8 ? 255.0 : 65535.0) + (a.dark ? c->dark_absmax : 0.0);
+        const double den = a.flat ? c->flat_absmin : 1.0;
+        a.no_overflow = (num / den < 3.0e38) ? 1 : 0;
+    }
     a.pred = make_predicate(thr, cond == IMGCORR_COND_LT ? COND_LT : COND_GT);
     return IMGCORR_OK;
 }
@@ -298,7 +346,7 @@ extern "C" IMGCORR_API int imgcorr_pointwise_median(imgcorr_ctx* c, const void* 
                                         int flags, void* stream) {
     GUARD(c);
     K1Args a;
-    int r = fill_k1(c, a, raw_dev, out_dev, mask_dev, n_frames, threshold, ksize, cond, flags);
+    int r = fill_k1(c, a, raw_dev, raw_dtype, out_dev, mask_dev, n_frames, threshold, ksize, cond, flags);
     if (r) return r;
     int l = 0;
     cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, c->k1_seg_rows, (cudaStream_t)stream, &l);
@@ -323,6 +371,7 @@ static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, 
     a.x0 = x0; a.y0 = y0; a.ow = ow; a.oh = oh;
     a.border = border_for_dtype(sdt == DT_U8, sdt == DT_U16, border);
     a.lens = c->lens;
+    a.lens_dev = c->lens_dev;
     int l = 0;
     cudaError_t e = launch_k2(a, sdt, ddt, c->k2_variant, st, &l);
     c->launches += l;
@@ -370,7 +419,7 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         if (x0 != 0 || y0 != 0 || ow != c->W || oh != c->H)
             return fail(IMGCORR_ERR_INVALID, "output window without a lens");
         K1Args a;
-        int r = fill_k1(c, a, raw, out, nullptr, n, thr, ksize, IMGCORR_COND_GT, flags);
+        int r = fill_k1(c, a, raw, raw_dtype, out, nullptr, n, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
         cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, c->k1_seg_rows, st, &l);
@@ -397,7 +446,7 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         const bool prof = c->profile > 0 && (c->chain_groups_seen++ % c->profile) == 0;
         if (prof) { c->prof_frames[0] += nf; c->prof_frames[1] += nf; }
         K1Args a;
-        int r = fill_k1(c, a, (const char*)raw + f * raw_stride, mid, nullptr, nf, thr, ksize, IMGCORR_COND_GT, flags);
+        int r = fill_k1(c, a, (const char*)raw + f * raw_stride, raw_dtype, mid, nullptr, nf, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
         if (prof) prof_mark(c, 0, st);

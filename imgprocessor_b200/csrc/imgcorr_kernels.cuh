@@ -22,17 +22,21 @@ struct K1Args {
     int H, W, n_frames;
     int ksize;              // 0 (pointwise only), 3, 5
     int maps_finite;        // dark / flat hold no NaN / inf (checked once at upload)
+    const float* flat_nz;   // copy of flat with zeros replaced by 1.0 (unconditional division), or null
+    int no_overflow;        // the calibration proves |raw - dark| / |flat| < FLT_MAX for this raw dtype: nan_to_num is the identity
     PointwiseConst pw;
     PredicateConst pred;
 };
 
 // variant: 0 = pick automatically, 1 = generic tiles (plain coalesced loads), 2 = TMA-staged tiles,
-//          3 = TMA streaming pipeline (3x3 only).  seg_rows: rows per work unit of the streaming kernel (0 = default)
+//          3 = TMA streaming pipeline (3x3 only), 4 = streaming pipeline v2 (two columns per lane; u16 / f32, 3x3).  seg_rows: rows per work unit of the streaming kernel (0 = default)
 cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count, int seg_rows,
                       cudaStream_t stream, int* launches);
 bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
+bool k1_stream2_eligible(const K1Args& a, int raw_dtype, int out_dtype);
+cudaError_t launch_k1_stream2(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 
 // K2: undistortion remap ---------------------------------------------------------------------
 struct K2Args {
@@ -44,7 +48,11 @@ struct K2Args {
     int x0, y0, ow, oh;     // output window in full-frame coordinates (keep_size=False crop)
     double border;
     LensConst lens;
+    const double* lens_dev;  // device copy of the lens constants (see LensPack), loaded once per thread into registers
 };
+
+// order of the doubles in K2Args::lens_dev
+enum LensPack : int { LP_K1, LP_K2, LP_K3, LP_P1, LP_P2, LP_P1X2, LP_P2X2, LP_FX, LP_FY, LP_CX, LP_CY, LP_IR0, LP_IR2, LP_IR4, LP_IR5, LP_PAD, LP_COUNT };
 
 cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t stream,
                       int* launches);

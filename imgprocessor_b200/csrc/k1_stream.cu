@@ -24,8 +24,18 @@ namespace imgcorr {
 constexpr int KS_CW = 4;                    // consumer warps per CTA
 constexpr int KS_SW = 30;                   // output columns per consumer warp
 constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
-constexpr int KS_R = 8;                     // rows per pipeline stage
-constexpr int KS_NSTAGE = 4;
+#ifndef KS_R_V
+#define KS_R_V 8
+#endif
+#ifndef KS_NSTAGE_V
+#define KS_NSTAGE_V 4
+#endif
+#ifndef KS_MINB_V
+#define KS_MINB_V 5
+#endif
+constexpr int KS_R = KS_R_V;                // rows per pipeline stage
+constexpr int KS_NSTAGE = KS_NSTAGE_V;
+constexpr int KS_MINB = KS_MINB_V;          // CTAs per SM the register allocation aims at
 constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
 constexpr int KS_MAPX = 4;
 constexpr int KS_THREADS = (KS_CW + 1) * 32;
@@ -83,6 +93,12 @@ template <> __device__ __forceinline__ float    ks_out<float>(float v)    { retu
 template <> __device__ __forceinline__ uint16_t ks_out<uint16_t>(float v) { return sat_u16(v); }
 template <> __device__ __forceinline__ uint8_t  ks_out<uint8_t>(float v)  { return sat_u8(v); }
 
+__device__ __noinline__ bool ks_exact(float x, float b, double thr, int cond) {
+    PredicateConst pc;
+    pc.thr = thr; pc.cond = cond; pc.lo = 0.f; pc.hi = 0.f; pc.fast_ok = 0;
+    return predicate_exact((double)x, (double)b, pc);
+}
+
 struct UnitGeom {
     int frame, tx0, ys, ye, yl0, n_in, nchunk;
 };
@@ -104,11 +120,12 @@ __device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int 
 
 // CFG >= 0 bakes the per-launch switches into the instruction stream (the kernel is issue bound: every
 // per-row flag test costs); CFG < 0 reads them from the arguments.
-enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32 };
+enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32, KS_NZ = 64 };
+// KS_NZ: a.flat is the zero-free copy (zeros replaced by 1.0) -> unconditional division
 // KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
 
 template <typename RawT, typename OutT, int CFG>
-__global__ void __launch_bounds__(KS_THREADS)
+__global__ void __launch_bounds__(KS_THREADS, KS_MINB)
 k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_dark,
                  const __grid_constant__ CUtensorMap tm_flat, K1Args a, int strips, int segs, int seg_rows, int total_units) {
     using B = StreamBox<RawT>;
@@ -124,8 +141,10 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                                : a.pw.flags;
     const int H = a.H, W = a.W;
 
+    float* sconst = (float*)(smem + B::bar_off + 2 * KS_NSTAGE * sizeof(uint64_t));      // lo, hi, thr (double)
     if (threadIdx.x == 0) {
         for (int s = 0; s < KS_NSTAGE; ++s) { ks_bar_init(&full[s], 1); ks_bar_init(&empty[s], KS_CW); }
+        sconst[0] = a.pred.lo; sconst[1] = a.pred.hi; *(double*)(sconst + 2) = a.pred.thr;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -154,7 +173,9 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 
     // ---------------------------------------------------------------------- consumers
     const PointwiseConst pw = a.pw;
+    // per-launch constants come from shared memory: ptxas would re-read kernel parameters at every use
     PredicateConst pred = a.pred;
+    pred.lo = sconst[0]; pred.hi = sconst[1]; pred.thr = *(const double*)(sconst + 2);
     if (CFG >= 0) pred.cond = (CFG & KS_LT) ? COND_LT : COND_GT;
     const int lc = warp * KS_SW - 1 + lane;            // strip-local column of this lane: -1 .. 120
     uint32_t g = 0;
@@ -184,17 +205,26 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
             double rd; float ra;
             StreamRaw<RawT>::ld(rv, rd, ra);
             bool ok;
-            float x = pointwise_fast(flags, rd, ra, d, f, ok);
+            float x = (CFG >= 0 && (CFG & KS_NZ)) ? pointwise_fast_nz(flags, rd, ra, d, f, ok) : pointwise_fast(flags, rd, ra, d, f, ok);
             if (check) { if (!ok) x = pointwise<float>(pw, rd, d, 0.0f, f); }
             return x;
         };
         auto emit = [&](const Sorted3<float>& t2, bool on) {
             const float med = median9(s0, s1, t2);
             bool rep;
-            if (!predicate_certain(c1, med, pred, rep)) rep = predicate_exact((double)c1, (double)med, pred);
+            const bool sure = predicate_certain(c1, med, pred, rep);
             if (on) {
                 *outp = ks_out<OutT>(rep ? med : c1);
                 if (has_mask) *maskp = rep ? 1 : 0;
+            }
+            // ~1e-5 of the pixels fall inside the guard band of the float32 test: those lanes evaluate the reference's
+            // float64 expression out of line and overwrite their result (one warp-uniform branch in the common case)
+            if (__any_sync(0xffffffffu, !sure)) {
+                if (!sure && on) {
+                    const bool r2 = ks_exact(c1, med, pred.thr, pred.cond);
+                    *outp = ks_out<OutT>(r2 ? med : c1);
+                    if (has_mask) *maskp = r2 ? 1 : 0;
+                }
             }
         };
         auto row = [&](const uint8_t* base, int j) {
@@ -288,27 +318,31 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
 }
 
 template <typename RawT, typename OutT>
-static cudaError_t launch_stream_t(const K1Args& a, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
+static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
     using B = StreamBox<RawT>;
+    K1Args a = a_in;
+    // pick the instantiation: the hot configurations are fully specialised, the rest read their flags at run time
+    const bool check = !a.maps_finite || sizeof(RawT) == 4;
+    const int f = a.pw.flags;
+    const bool chain = a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
+                       a.pred.cond == COND_GT;
+    const bool plain = !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
+    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
+    int slot;
+    if (chain) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
+    if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ>; slot = 0; }
+    else if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ>; slot = 1; }
+    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK>; slot = 2; }
+    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK>; slot = 3; }
+    else { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 4; }
+
     CUtensorMap tr, td, tf;
     if (!ks_make_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
     if (!ks_make_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.dark)
         return cudaErrorInvalidValue;
     if (!ks_make_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
-    // pick the instantiation: the two hot configurations are fully specialised, the rest read their flags at run time
-    const bool check = !a.maps_finite || sizeof(RawT) == 4;
-    const int f = a.pw.flags;
-    const bool chain = a.dark && a.flat && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
-                       a.pred.cond == COND_GT;
-    const bool plain = !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
-    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
-    int slot;
-    if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N>; slot = 0; }
-    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_CHECK>; slot = 1; }
-    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK>; slot = 2; }
-    else { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 3; }
-    static int per_sm[4] = {0, 0, 0, 0};
+    static int per_sm[5] = {0, 0, 0, 0, 0};
     if (!per_sm[slot]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
         if (e != cudaSuccess) return e;
@@ -317,12 +351,27 @@ static cudaError_t launch_stream_t(const K1Args& a, CUtensorMapDataType rdt, int
         per_sm[slot] = n < 1 ? 1 : n;
     }
     const int strips = (a.W + KS_TW - 1) / KS_TW;
-    if (seg_rows <= 0) seg_rows = 64;
+    const long long slots = (long long)sm_count * per_sm[slot];
+    if (seg_rows <= 0) {
+        // all units cost the same: pick the segment height whose unit count fills whole waves of the resident CTAs best,
+        // counting the two re-read halo rows per segment against it
+        double best = -1.0;
+        for (int waves = 1; waves <= 8; ++waves) {
+            long long segs_try = slots * waves / ((long long)strips * a.n_frames);
+            if (segs_try < 1) continue;
+            int rows = (int)((a.H + segs_try - 1) / segs_try);
+            if (rows < 2 * KS_R) rows = 2 * KS_R;
+            const long long units = (long long)strips * ((a.H + rows - 1) / rows) * a.n_frames;
+            const double util = (double)units / (double)(((units + slots - 1) / slots) * slots) * rows / (rows + 2.0);
+            if (util > best) { best = util; seg_rows = rows; }
+        }
+        if (seg_rows <= 0) seg_rows = a.H;
+    }
     if (seg_rows < 4) seg_rows = 4;
     const int segs = (a.H + seg_rows - 1) / seg_rows;
     const long long total = (long long)strips * segs * a.n_frames;
     if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-    long long grid = (long long)sm_count * per_sm[slot];
+    long long grid = slots;
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, KS_THREADS, B::total, st>>>(tr, td, tf, a, strips, segs, seg_rows, (int)total);
     return cudaGetLastError();

@@ -18,80 +18,98 @@
 
 namespace imgcorr {
 
-constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = 4;     // CTA = 32 x 8 threads, tile = 32 x 32 outputs
+constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = 8;     // CTA = 32 x 8 threads, tile = 32 x 64 outputs
 
 template <typename SrcT> __device__ __forceinline__ SrcT border_cast(double b) { return (SrcT)b; }
 
+// per-pixel interpolation weights, computed once and applied to every frame of the launch
+template <typename SrcT> struct Weights {        // float32 / uint16 / float64 images: OpenCV's float32 table entry
+    float w00, w01, w10, w11;
+    __device__ __forceinline__ void set(const FixedCoord& c) { bilinear_weights(c.fx, c.fy, w00, w01, w10, w11); }
+};
+template <> struct Weights<uint8_t> {            // uint8 images: int16 fixed-point weights
+    int fx, fy;
+    __device__ __forceinline__ void set(const FixedCoord& c) { fx = c.fx; fy = c.fy; }
+};
+
 template <typename SrcT, typename DstT> struct Blend;
 template <> struct Blend<float, float> {
-    static __device__ __forceinline__ float run(float a, float b, float c, float d, const FixedCoord& fc) {
-        float w00, w01, w10, w11; bilinear_weights(fc.fx, fc.fy, w00, w01, w10, w11);
-        return blend_f32(a, b, c, d, w00, w01, w10, w11);
+    static __device__ __forceinline__ float run(float a, float b, float c, float d, const Weights<float>& w) {
+        return blend_f32(a, b, c, d, w.w00, w.w01, w.w10, w.w11);
     }
 };
 template <> struct Blend<float, double> {
-    static __device__ __forceinline__ double run(float a, float b, float c, float d, const FixedCoord& fc) {
-        return (double)Blend<float, float>::run(a, b, c, d, fc);
+    static __device__ __forceinline__ double run(float a, float b, float c, float d, const Weights<float>& w) {
+        return (double)blend_f32(a, b, c, d, w.w00, w.w01, w.w10, w.w11);
     }
 };
 template <> struct Blend<double, double> {
-    static __device__ __forceinline__ double run(double a, double b, double c, double d, const FixedCoord& fc) {
-        float w00, w01, w10, w11; bilinear_weights(fc.fx, fc.fy, w00, w01, w10, w11);
-        return blend_f64(a, b, c, d, w00, w01, w10, w11);
+    static __device__ __forceinline__ double run(double a, double b, double c, double d, const Weights<double>& w) {
+        return blend_f64(a, b, c, d, w.w00, w.w01, w.w10, w.w11);
     }
 };
 template <> struct Blend<uint16_t, uint16_t> {
-    static __device__ __forceinline__ uint16_t run(uint16_t a, uint16_t b, uint16_t c, uint16_t d, const FixedCoord& fc) {
-        return sat_u16(Blend<float, float>::run((float)a, (float)b, (float)c, (float)d, fc));
+    static __device__ __forceinline__ uint16_t run(uint16_t a, uint16_t b, uint16_t c, uint16_t d, const Weights<uint16_t>& w) {
+        return sat_u16(blend_f32((float)a, (float)b, (float)c, (float)d, w.w00, w.w01, w.w10, w.w11));
     }
 };
 template <> struct Blend<uint8_t, uint8_t> {
-    static __device__ __forceinline__ uint8_t run(uint8_t a, uint8_t b, uint8_t c, uint8_t d, const FixedCoord& fc) {
-        return (uint8_t)blend_u8(a, b, c, d, fc.fx, fc.fy);
+    static __device__ __forceinline__ uint8_t run(uint8_t a, uint8_t b, uint8_t c, uint8_t d, const Weights<uint8_t>& w) {
+        return (uint8_t)blend_u8(a, b, c, d, w.fx, w.fy);
     }
 };
 
+// rim of the image: any neighbour outside [0,W)x[0,H) is the border value; a window entirely outside is the border
+// value itself (OpenCV does not blend it).  Rare -> kept out of line so the hot path stays small.
 template <typename SrcT, typename DstT>
-__device__ __forceinline__ DstT remap_pixel(const SrcT* __restrict__ src, int H, int W, const FixedCoord& c, SrcT bval) {
-    const int ix = c.ix, iy = c.iy;
-    SrcT v00, v01, v10, v11;
-    if ((unsigned)ix < (unsigned)(W - 1) && (unsigned)iy < (unsigned)(H - 1)) {
-        const SrcT* p = src + (size_t)iy * W + ix;
-        v00 = __ldg(p); v01 = __ldg(p + 1); v10 = __ldg(p + W); v11 = __ldg(p + W + 1);
-    } else {
-        // OpenCV: a window entirely outside the image is the border value itself, not a blend of it
-        if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return (DstT)bval;
-        const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
-        const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
-        const SrcT* p = src + (ptrdiff_t)iy * W + ix;
-        v00 = (x0 && y0) ? __ldg(p) : bval;
-        v01 = (x1 && y0) ? __ldg(p + 1) : bval;
-        v10 = (x0 && y1) ? __ldg(p + W) : bval;
-        v11 = (x1 && y1) ? __ldg(p + W + 1) : bval;
-    }
-    return Blend<SrcT, DstT>::run(v00, v01, v10, v11, c);
+__device__ __noinline__ DstT remap_rim(const SrcT* __restrict__ src, int H, int W, int ix, int iy, Weights<SrcT> w, SrcT bval) {
+    if (ix >= W || ix + 1 < 0 || iy >= H || iy + 1 < 0) return (DstT)bval;
+    const bool x0 = (unsigned)ix < (unsigned)W, x1 = (unsigned)(ix + 1) < (unsigned)W;
+    const bool y0 = (unsigned)iy < (unsigned)H, y1 = (unsigned)(iy + 1) < (unsigned)H;
+    const SrcT* p = src + (ptrdiff_t)iy * W + ix;
+    const SrcT v00 = (x0 && y0) ? __ldg(p) : bval;
+    const SrcT v01 = (x1 && y0) ? __ldg(p + 1) : bval;
+    const SrcT v10 = (x0 && y1) ? __ldg(p + W) : bval;
+    const SrcT v11 = (x1 && y1) ? __ldg(p + W + 1) : bval;
+    return Blend<SrcT, DstT>::run(v00, v01, v10, v11, w);
 }
 
 // MODE: 0 explicit maps, 1 analytic general P, 2 analytic separable P^-1 (x = x(u), y = y(v))
 template <typename SrcT, typename DstT, int MODE>
-__global__ void __launch_bounds__(K2_BX * K2_BY) k2_remap_kernel(K2Args a) {
+__global__ void __launch_bounds__(K2_BX * K2_BY, 3) k2_remap_kernel(K2Args a) {
     const int ox = blockIdx.x * K2_BX + (threadIdx.x % K2_BX);
     const int ty = threadIdx.x / K2_BX;
     if (ox >= a.ow) return;
     const int u = ox + a.x0;
     const SrcT bval = border_cast<SrcT>(a.border);
-    const size_t src_stride = (size_t)a.H * a.W, dst_stride = (size_t)a.oh * a.ow;
-    const int H = a.H, W = a.W, nf = a.n_frames;
-    const LensConst L = a.lens;
+    const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
+    const int src_stride = H * W, dst_stride = oh * ow;      // elements; frames are < 2^31 pixels (32767^2)
+    // lens constants live in registers for the whole thread.  They are read from a small device buffer, not from
+    // the kernel parameters: ptxas re-materialises parameter loads at every use (one LDC per use, ~16 issue
+    // slots per pixel in this issue-bound kernel); a global load it has to keep.
+    LensConst L = a.lens;
+    if (MODE == 2) {
+        const double2* lp = reinterpret_cast<const double2*>(a.lens_dev);
+        double2 q;
+        q = __ldg(lp + 0); L.k1 = q.x; L.k2 = q.y;
+        q = __ldg(lp + 1); L.k3 = q.x; L.p1 = q.y;
+        q = __ldg(lp + 2); L.p2 = q.x; L.p1x2 = q.y;
+        q = __ldg(lp + 3); L.p2x2 = q.x; L.fx = q.y;
+        q = __ldg(lp + 4); L.fy = q.x; L.cx = q.y;
+        q = __ldg(lp + 5); L.cy = q.x; L.ir[0] = q.y;
+        q = __ldg(lp + 6); L.ir[2] = q.x; L.ir[4] = q.y;
+        q = __ldg(lp + 7); L.ir[5] = q.x;
+    }
     double xc = 0.0, xc2 = 0.0;
     if (MODE == 2) {
         xc = fma((double)u, L.ir[0], L.ir[2]);
         xc2 = dmul(xc, xc);
     }
+    const int oy0 = blockIdx.y * (K2_BY * K2_ROWS) + ty;
 #pragma unroll
     for (int j = 0; j < K2_ROWS; ++j) {
-        const int oy = blockIdx.y * (K2_BY * K2_ROWS) + ty + j * K2_BY;
-        if (oy >= a.oh) break;
+        const int oy = oy0 + j * K2_BY;
+        if (oy >= oh) break;
         const int v = oy + a.y0;
         float mx, my;
         if (MODE == 2) {
@@ -100,16 +118,29 @@ __global__ void __launch_bounds__(K2_BX * K2_BY) k2_remap_kernel(K2Args a) {
         } else if (MODE == 1) {
             undistort_map(L, u, v, mx, my);
         } else {
-            mx = __ldg(a.mapx + (size_t)v * W + u);
-            my = __ldg(a.mapy + (size_t)v * W + u);
+            mx = __ldg(a.mapx + v * W + u);
+            my = __ldg(a.mapy + v * W + u);
         }
         const FixedCoord c = fixed_coord(mx, my);
-        const SrcT* src = (const SrcT*)a.src;
-        DstT* dst = (DstT*)a.dst + (size_t)oy * a.ow + ox;
-        for (int f = 0; f < nf; ++f) {
-            *dst = remap_pixel<SrcT, DstT>(src, H, W, c, bval);
-            src += src_stride;
-            dst += dst_stride;
+        Weights<SrcT> w;
+        w.set(c);
+        DstT* dst = (DstT*)a.dst + (oy * ow + ox);
+        if ((unsigned)c.ix < (unsigned)(W - 1) && (unsigned)c.iy < (unsigned)(H - 1)) {
+            const SrcT* p = (const SrcT*)a.src + (c.iy * W + c.ix);
+#pragma unroll 1
+            for (int f = 0; f < nf; ++f) {
+                *dst = Blend<SrcT, DstT>::run(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), w);
+                p += src_stride;
+                dst += dst_stride;
+            }
+        } else {
+            const SrcT* src = (const SrcT*)a.src;
+#pragma unroll 1
+            for (int f = 0; f < nf; ++f) {
+                *dst = remap_rim<SrcT, DstT>(src, H, W, c.ix, c.iy, w, bval);
+                src += src_stride;
+                dst += dst_stride;
+            }
         }
     }
 }
@@ -141,6 +172,7 @@ cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant
     if (a.H > 32767 || a.W > 32767) return cudaErrorInvalidValue;      // OpenCV's remap itself is limited to short coordinates
     if (a.x0 < 0 || a.y0 < 0 || a.x0 + a.ow > a.W || a.y0 + a.oh > a.H) return cudaErrorInvalidValue;
     if ((a.mapx == nullptr) != (a.mapy == nullptr)) return cudaErrorInvalidValue;
+    if (!a.mapx && !a.lens_dev) return cudaErrorInvalidValue;
     if (launches) ++*launches;
     if (src_dtype == DT_F32 && dst_dtype == DT_F32) return launch_t<float, float>(a, st);
     if (src_dtype == DT_F32 && dst_dtype == DT_F64) return launch_t<float, double>(a, st);

@@ -81,6 +81,7 @@ void emul_k1(const void* raw, int raw_dtype, const float* dark, const float* asc
 static bool make_lens(const double* K, const double* dist, const double* P, LensConst& L) {
     if (!invert3x3(P, L.ir)) return false;
     L.k1 = dist[0]; L.k2 = dist[1]; L.p1 = dist[2]; L.p2 = dist[3]; L.k3 = dist[4];
+    L.p1x2 = L.p1 + L.p1; L.p2x2 = L.p2 + L.p2;
     L.fx = K[0]; L.fy = K[4]; L.cx = K[2]; L.cy = K[5];
     L.affine = (L.ir[6] == 0.0 && L.ir[7] == 0.0 && L.ir[8] == 1.0) ? 1 : 0;
     return true;

@@ -66,20 +66,35 @@ def test_k1_bit_exact_generic(ip, shape, dtype, ksize):
 
 @pytest.mark.parametrize('shape', [(5, 16), (33, 144), (96, 128), (70, 272), (300, 528), (257, 1024), (64, 4096)])
 @pytest.mark.parametrize('dtype', [np.uint8, np.uint16, np.float32])
-@pytest.mark.parametrize('ksize,variant', [(3, 2), (5, 2), (3, 3)])
+@pytest.mark.parametrize('ksize,variant', [(3, 2), (5, 2), (3, 3), (3, 4)])
 def test_k1_bit_exact_tma(ip, shape, dtype, ksize, variant):
-    """variant 2 = TMA-staged tiles, 3 = TMA streaming pipeline (3x3)"""
+    """variant 2 = TMA-staged tiles, 3 / 4 = TMA streaming pipeline v1 / v2 (3x3)"""
     H, W = shape
+    if variant == 4 and dtype == np.uint8:
+        pytest.skip('streaming v2 serves uint16 / float32 frames')
     raw, dark, flat = _case(H, W, 4, dtype)
     e = _eng(ip, H, W, variant)
     e.set_dark(dark)
     e.set_flat(flat)
-    out, mask = e.pointwise_median(_dev(raw), 0.1, ksize, want_mask=True)
     x = models.pointwise_model(raw, dark, flat, nan_to_num=True)
     want, wmask = models.median_threshold_model(x, 0.1, ksize)
-    assert np.array_equal(out.cpu().numpy(), want)
-    assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
-    # partial calibrations through the TMA path as well
+    if variant == 4:
+        out, _ = e.pointwise_median(_dev(raw), 0.1, ksize)                    # chain specialisation (no mask)
+        assert np.array_equal(out.cpu().numpy(), want)
+        e.set_dark(None)
+        e.set_flat(None)
+        out, mask = e.pointwise_median(_dev(raw), 0.1, ksize, flags=0, want_mask=True)     # plain median + mask
+        w2, m2 = models.median_threshold_model(models.pointwise_model(raw, None, None, False), 0.1, ksize)
+        assert np.array_equal(out.cpu().numpy(), w2) and np.array_equal(mask.cpu().numpy().astype(bool), m2)
+        e.set_dark(dark)
+        e.set_flat(flat)
+    else:
+        out, mask = e.pointwise_median(_dev(raw), 0.1, ksize, want_mask=True)
+        assert np.array_equal(out.cpu().numpy(), want)
+        assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    # partial calibrations through the TMA path as well (v2 has no such specialisation: auto-dispatch falls back)
+    if variant == 4:
+        e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
     e.set_dark(None)
     out, _ = e.pointwise_median(_dev(raw), 0.1, ksize)
     want, _ = models.median_threshold_model(models.pointwise_model(raw, None, flat, True), 0.1, ksize)
@@ -95,6 +110,38 @@ def test_k1_tma_refused_when_not_eligible(ip):
         e = _eng(ip, 33, 130, variant)
         with pytest.raises(ip.lib_mod.ImgcorrError):
             e.pointwise_median(_dev(np.zeros((33, 130), np.uint16)), 0.1, 3)
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
+@pytest.mark.parametrize('seg_rows', [4, 5, 7, 8, 9, 16, 33, 1000])
+@pytest.mark.parametrize('W', [256, 240, 248, 496, 504, 1000])
+def test_k1_stream2_seams_and_strip_edges(ip, seg_rows, W):
+    """streaming v2: row segments and 248-column strips meet without seams, the right frame edge may fall anywhere
+    inside a strip / warp; tiny flats make the quotient overflow (clamp path), non-finite maps take the check path"""
+    H = 41
+    raw, dark, flat = _case(H, W, 8, np.uint16)
+    e = _eng(ip, H, W, 4)
+    e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, seg_rows)
+    for tweak in ('plain', 'overflow', 'nonfinite'):
+        d2, f2 = dark.copy(), flat.copy()
+        if tweak == 'overflow':
+            f2[3, 5] = np.float32(1e-42)
+            f2[H - 1, W - 1] = np.float32(-1e-40)
+        if tweak == 'nonfinite':
+            f2[7, 9], f2[8, 9], d2[20, 20] = np.inf, np.nan, -np.inf
+        e.set_dark(d2)
+        e.set_flat(f2)
+        out, _ = e.pointwise_median(_dev(raw), 0.1, 3)
+        want, _ = models.median_threshold_model(models.pointwise_model(raw, d2, f2, True), 0.1, 3)
+        assert np.array_equal(out.cpu().numpy(), want), tweak
+    rawf = synth.scene(H, W, 9, np.float32)
+    rawf[5, 5], rawf[6, 7] = np.inf, np.nan
+    e.set_dark(dark)
+    e.set_flat(flat)
+    out, _ = e.pointwise_median(_dev(rawf), 0.1, 3)
+    want, _ = models.median_threshold_model(models.pointwise_model(rawf, dark, flat, True), 0.1, 3)
+    assert np.array_equal(out.cpu().numpy(), want)
+    e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, 0)
     e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
 
 
@@ -468,7 +515,7 @@ def test_config1_1024_f32_full_chain(ip):
     assert (out != want).sum() == 0
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3])
+@pytest.mark.parametrize('variant', [1, 2, 3, 4])
 def test_config2_4096x3000_u16_k1(ip, variant):
     """configs[1]: a 4096x3000 uint16 frame through K1, bit-exact against the oracle at full size."""
     H, W = 3000, 4096
@@ -476,11 +523,12 @@ def test_config2_4096x3000_u16_k1(ip, variant):
     e = _eng(ip, H, W, variant)
     e.set_dark(dark)
     e.set_flat(flat)
-    out, mask = e.pointwise_median(_dev(raw), 0.1, 3, want_mask=True)
+    out, mask = e.pointwise_median(_dev(raw), 0.1, 3, want_mask=variant != 4)
     x = models.pointwise_model(raw, dark, flat, True)
     want, wmask = models.median_threshold_model(x, 0.1, 3)
     assert np.array_equal(out.cpu().numpy(), want)
-    assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    if mask is not None:
+        assert np.array_equal(mask.cpu().numpy().astype(bool), wmask)
     assert 0.001 < wmask.mean() < 0.05
     e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
 
