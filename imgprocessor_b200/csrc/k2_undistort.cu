@@ -18,7 +18,14 @@
 
 namespace imgcorr {
 
-constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = 8;     // CTA = 32 x 8 threads, tile = 32 x 64 outputs
+#ifndef K2_ROWS_V
+#define K2_ROWS_V 4
+#endif
+#ifndef K2_MINB_V
+#define K2_MINB_V 4
+#endif
+constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = K2_ROWS_V;     // CTA = 32 x 8 threads, tile = 32 x (8 * K2_ROWS) outputs
+constexpr int K2_MINB = K2_MINB_V;
 
 template <typename SrcT> __device__ __forceinline__ SrcT border_cast(double b) { return (SrcT)b; }
 
@@ -75,8 +82,13 @@ __device__ __noinline__ DstT remap_rim(const SrcT* __restrict__ src, int H, int 
 }
 
 // MODE: 0 explicit maps, 1 analytic general P, 2 analytic separable P^-1 (x = x(u), y = y(v))
+//
+// The kernel is bound by the latency of the four-neighbour gathers, not by the float64 map evaluation (with explicit
+// maps it is no faster, see profiles/).  So a thread first computes the coordinates of all its K2_ROWS pixels, then
+// issues all 4*K2_ROWS gathers unconditionally (pixels on the rim gather from offset 0 and are redone out of line),
+// then blends and stores: 4*K2_ROWS loads in flight per thread instead of 4.
 template <typename SrcT, typename DstT, int MODE>
-__global__ void __launch_bounds__(K2_BX * K2_BY, 3) k2_remap_kernel(K2Args a) {
+__global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args a) {
     const int ox = blockIdx.x * K2_BX + (threadIdx.x % K2_BX);
     const int ty = threadIdx.x / K2_BX;
     if (ox >= a.ow) return;
@@ -86,7 +98,7 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, 3) k2_remap_kernel(K2Args a) {
     const int src_stride = H * W, dst_stride = oh * ow;      // elements; frames are < 2^31 pixels (32767^2)
     // lens constants live in registers for the whole thread.  They are read from a small device buffer, not from
     // the kernel parameters: ptxas re-materialises parameter loads at every use (one LDC per use, ~16 issue
-    // slots per pixel in this issue-bound kernel); a global load it has to keep.
+    // slots per pixel); a global load it has to keep.
     LensConst L = a.lens;
     if (MODE == 2) {
         const double2* lp = reinterpret_cast<const double2*>(a.lens_dev);
@@ -106,11 +118,14 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, 3) k2_remap_kernel(K2Args a) {
         xc2 = dmul(xc, xc);
     }
     const int oy0 = blockIdx.y * (K2_BY * K2_ROWS) + ty;
+
+    int off[K2_ROWS];            // element offset of the top-left neighbour; 0 for rim pixels (redone below)
+    int frac[K2_ROWS];           // fx | fy << 8 | inner << 16 | row valid << 17
+    int cix[K2_ROWS], ciy[K2_ROWS];
 #pragma unroll
     for (int j = 0; j < K2_ROWS; ++j) {
         const int oy = oy0 + j * K2_BY;
-        if (oy >= oh) break;
-        const int v = oy + a.y0;
+        const int v = (oy < oh ? oy : oh - 1) + a.y0;
         float mx, my;
         if (MODE == 2) {
             const double y = fma((double)v, L.ir[4], L.ir[5]);
@@ -122,26 +137,45 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, 3) k2_remap_kernel(K2Args a) {
             my = __ldg(a.mapy + v * W + u);
         }
         const FixedCoord c = fixed_coord(mx, my);
-        Weights<SrcT> w;
-        w.set(c);
-        DstT* dst = (DstT*)a.dst + (oy * ow + ox);
-        if ((unsigned)c.ix < (unsigned)(W - 1) && (unsigned)c.iy < (unsigned)(H - 1)) {
-            const SrcT* p = (const SrcT*)a.src + (c.iy * W + c.ix);
+        const bool inner = (unsigned)c.ix < (unsigned)(W - 1) && (unsigned)c.iy < (unsigned)(H - 1);
+        off[j] = inner ? c.iy * W + c.ix : 0;
+        frac[j] = c.fx | (c.fy << 8) | (inner ? 1 << 16 : 0) | (oy < oh ? 1 << 17 : 0);
+        cix[j] = c.ix; ciy[j] = c.iy;
+    }
+
+    const SrcT* src = (const SrcT*)a.src;
+    DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
+    const bool tiny = W < 2 || H < 2;                     // no interior 2x2 window exists: offset 0 + 1 + W would overrun
+    // software pipeline over the frames of the launch: the gathers of frame f+1 are in flight while frame f is blended
+    SrcT v00[K2_ROWS], v01[K2_ROWS], v10[K2_ROWS], v11[K2_ROWS];
+    auto gather = [&](const SrcT* s) {
+#pragma unroll
+        for (int j = 0; j < K2_ROWS; ++j) {
+            const SrcT* p = s + off[j];
+            v00[j] = __ldg(p); v01[j] = __ldg(p + 1); v10[j] = __ldg(p + W); v11[j] = __ldg(p + W + 1);
+        }
+    };
+    if (!tiny) gather(src);
 #pragma unroll 1
-            for (int f = 0; f < nf; ++f) {
-                *dst = Blend<SrcT, DstT>::run(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), w);
-                p += src_stride;
-                dst += dst_stride;
-            }
-        } else {
-            const SrcT* src = (const SrcT*)a.src;
-#pragma unroll 1
-            for (int f = 0; f < nf; ++f) {
-                *dst = remap_rim<SrcT, DstT>(src, H, W, c.ix, c.iy, w, bval);
-                src += src_stride;
-                dst += dst_stride;
+    for (int f = 0; f < nf; ++f) {
+        SrcT c00[K2_ROWS], c01[K2_ROWS], c10[K2_ROWS], c11[K2_ROWS];
+#pragma unroll
+        for (int j = 0; j < K2_ROWS; ++j) { c00[j] = v00[j]; c01[j] = v01[j]; c10[j] = v10[j]; c11[j] = v11[j]; }
+        if (f + 1 < nf && !tiny) gather(src + src_stride);
+#pragma unroll
+        for (int j = 0; j < K2_ROWS; ++j) {
+            if (frac[j] & (1 << 17)) {
+                FixedCoord c; c.ix = cix[j]; c.iy = ciy[j]; c.fx = frac[j] & 31; c.fy = (frac[j] >> 8) & 31;
+                Weights<SrcT> w;
+                w.set(c);
+                DstT r;
+                if (frac[j] & (1 << 16)) r = Blend<SrcT, DstT>::run(c00[j], c01[j], c10[j], c11[j], w);
+                else r = remap_rim<SrcT, DstT>(src, H, W, c.ix, c.iy, w, bval);
+                dst[j * K2_BY * ow] = r;
             }
         }
+        src += src_stride;
+        dst += dst_stride;
     }
 }
 
