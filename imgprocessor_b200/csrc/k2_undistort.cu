@@ -19,10 +19,10 @@
 namespace imgcorr {
 
 #ifndef K2_ROWS_V
-#define K2_ROWS_V 4
+#define K2_ROWS_V 2
 #endif
 #ifndef K2_MINB_V
-#define K2_MINB_V 4
+#define K2_MINB_V 5
 #endif
 constexpr int K2_BX = 32, K2_BY = 8, K2_ROWS = K2_ROWS_V;     // CTA = 32 x 8 threads, tile = 32 x (8 * K2_ROWS) outputs
 constexpr int K2_MINB = K2_MINB_V;
@@ -119,9 +119,10 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
     }
     const int oy0 = blockIdx.y * (K2_BY * K2_ROWS) + ty;
 
-    int off[K2_ROWS];            // element offset of the top-left neighbour; 0 for rim pixels (redone below)
-    int frac[K2_ROWS];           // fx | fy << 8 | inner << 16 | row valid << 17
+    int off[K2_ROWS];            // element offset of the top-left neighbour; 0 for rim pixels (done in the second pass)
     int cix[K2_ROWS], ciy[K2_ROWS];
+    Weights<SrcT> wt[K2_ROWS];
+    unsigned rim = 0, live = 0;  // bit j: pixel j lies on the rim / row j exists
 #pragma unroll
     for (int j = 0; j < K2_ROWS; ++j) {
         const int oy = oy0 + j * K2_BY;
@@ -139,43 +140,44 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
         const FixedCoord c = fixed_coord(mx, my);
         const bool inner = (unsigned)c.ix < (unsigned)(W - 1) && (unsigned)c.iy < (unsigned)(H - 1);
         off[j] = inner ? c.iy * W + c.ix : 0;
-        frac[j] = c.fx | (c.fy << 8) | (inner ? 1 << 16 : 0) | (oy < oh ? 1 << 17 : 0);
         cix[j] = c.ix; ciy[j] = c.iy;
+        wt[j].set(c);
+        if (oy < oh) { live |= 1u << j; if (!inner) rim |= 1u << j; }
     }
 
-    const SrcT* src = (const SrcT*)a.src;
-    DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
     const bool tiny = W < 2 || H < 2;                     // no interior 2x2 window exists: offset 0 + 1 + W would overrun
-    // software pipeline over the frames of the launch: the gathers of frame f+1 are in flight while frame f is blended
-    SrcT v00[K2_ROWS], v01[K2_ROWS], v10[K2_ROWS], v11[K2_ROWS];
-    auto gather = [&](const SrcT* s) {
-#pragma unroll
-        for (int j = 0; j < K2_ROWS; ++j) {
-            const SrcT* p = s + off[j];
-            v00[j] = __ldg(p); v01[j] = __ldg(p + 1); v10[j] = __ldg(p + W); v11[j] = __ldg(p + W + 1);
-        }
-    };
-    if (!tiny) gather(src);
+    if (!tiny) {
+        const SrcT* src = (const SrcT*)a.src;
+        DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
+        const unsigned fast = live & ~rim;
 #pragma unroll 1
-    for (int f = 0; f < nf; ++f) {
-        SrcT c00[K2_ROWS], c01[K2_ROWS], c10[K2_ROWS], c11[K2_ROWS];
+        for (int f = 0; f < nf; ++f) {
+            SrcT v00[K2_ROWS], v01[K2_ROWS], v10[K2_ROWS], v11[K2_ROWS];
 #pragma unroll
-        for (int j = 0; j < K2_ROWS; ++j) { c00[j] = v00[j]; c01[j] = v01[j]; c10[j] = v10[j]; c11[j] = v11[j]; }
-        if (f + 1 < nf && !tiny) gather(src + src_stride);
-#pragma unroll
-        for (int j = 0; j < K2_ROWS; ++j) {
-            if (frac[j] & (1 << 17)) {
-                FixedCoord c; c.ix = cix[j]; c.iy = ciy[j]; c.fx = frac[j] & 31; c.fy = (frac[j] >> 8) & 31;
-                Weights<SrcT> w;
-                w.set(c);
-                DstT r;
-                if (frac[j] & (1 << 16)) r = Blend<SrcT, DstT>::run(c00[j], c01[j], c10[j], c11[j], w);
-                else r = remap_rim<SrcT, DstT>(src, H, W, c.ix, c.iy, w, bval);
-                dst[j * K2_BY * ow] = r;
+            for (int j = 0; j < K2_ROWS; ++j) {
+                const SrcT* p = src + off[j];
+                v00[j] = __ldg(p); v01[j] = __ldg(p + 1); v10[j] = __ldg(p + W); v11[j] = __ldg(p + W + 1);
             }
+#pragma unroll
+            for (int j = 0; j < K2_ROWS; ++j)
+                if (fast & (1u << j)) dst[j * K2_BY * ow] = Blend<SrcT, DstT>::run(v00[j], v01[j], v10[j], v11[j], wt[j]);
+            src += src_stride;
+            dst += dst_stride;
         }
-        src += src_stride;
-        dst += dst_stride;
+    } else {
+        rim = live;
+    }
+    // second pass, rare: pixels whose 2x2 window touches or leaves the frame
+    if (rim) {
+        const SrcT* src = (const SrcT*)a.src;
+        DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
+        for (int f = 0; f < nf; ++f) {
+#pragma unroll
+            for (int j = 0; j < K2_ROWS; ++j)
+                if (rim & (1u << j)) dst[j * K2_BY * ow] = remap_rim<SrcT, DstT>(src, H, W, cix[j], ciy[j], wt[j], bval);
+            src += src_stride;
+            dst += dst_stride;
+        }
     }
 }
 
