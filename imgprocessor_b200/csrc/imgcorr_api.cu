@@ -50,6 +50,7 @@ struct imgcorr_ctx {
     bool has_lens = false;
     LensConst lens{};
     double* lens_dev = nullptr;
+    void* dump = nullptr;                     // scratch for stores of lanes that own no output pixel
     int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 1;
     long long chain_groups_seen = 0;
     double prof_frames[2] = {0.0, 0.0};
@@ -143,6 +144,7 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->mid[0]);
     cudaFree(c->mid[1]);
     cudaFree(c->lens_dev);
+    cudaFree(c->dump);
     for (int k = 0; k < 2; ++k) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     delete c;
     return IMGCORR_OK;
@@ -330,6 +332,8 @@ static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, int raw_dtype, vo
     a.pw.flags = f; a.pw.exposure_time = c->exposure; a.pw.max_value = c->maxval;
     a.maps_finite = ((!a.dark || c->dark_finite) && (!a.flat || c->flat_finite)) ? 1 : 0;
     a.flat_nz = a.flat ? c->flat_nz : nullptr;
+    if (!c->dump) CK(cudaMalloc(&c->dump, (size_t)4 << 20));
+    a.dump = c->dump;
     // integer frames: |raw - dark| <= raw_max + max|dark|; divided by min|flat| it must stay below FLT_MAX
     a.no_overflow = 0;
     if (a.maps_finite && (raw_dtype == DT_U8 || raw_dtype == DT_U16)) {

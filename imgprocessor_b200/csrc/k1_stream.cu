@@ -256,11 +256,41 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                 c1 = x;
             }
             const int rows = u.n_in - k * KS_R;
-            if (rows >= KS_R) {
+            if (k > 0 && rows >= KS_R) {
+                // steady state: every row emits; the store is unconditional (lanes without an output pixel write to
+                // a private scratch slot) and the guard-band test is only accumulated — if any lane of the warp hit the
+                // band in this chunk (rare), the chunk is redone below with the exact predicate.
+                const Sorted3<float> k0 = s0, k1 = s1;
+                const float kc = c1;
+                OutT* op = valid ? outp : (OutT*)a.dump + (size_t)blockIdx.x * KS_THREADS + threadIdx.x;
+                uint8_t* mp = has_mask ? (valid ? maskp : (uint8_t*)a.dump + (size_t)(gridDim.x + blockIdx.x) * KS_THREADS * sizeof(OutT) + threadIdx.x) : nullptr;
+                const int ostride = valid ? W : 0;
+                bool unsure = false;
 #pragma unroll
-                for (int j = 0; j < KS_R; ++j) row(base, j);
+                for (int j = 0; j < KS_R; ++j) {
+                    const float x = pixel(base, j);
+                    const float l = __shfl_up_sync(0xffffffffu, x, 1);
+                    const float r = __shfl_down_sync(0xffffffffu, x, 1);
+                    const Sorted3<float> t2 = sort3(l, x, r);
+                    const float med = median9(s0, s1, t2);
+                    bool rep;
+                    unsure |= !predicate_certain(c1, med, pred, rep);
+                    *op = ks_out<OutT>(rep ? med : c1);
+                    if (has_mask) { *mp = rep ? 1 : 0; mp += ostride; }
+                    op += ostride;
+                    s0 = s1; s1 = t2; c1 = x;
+                }
+                if (__any_sync(0xffffffffu, unsure)) {
+                    s0 = k0; s1 = k1; c1 = kc;
+                    for (int j = 0; j < KS_R; ++j) row(base, j);
+                } else {
+                    outp += (size_t)KS_R * W;
+                    if (has_mask) maskp += (size_t)KS_R * W;
+                    i += KS_R;
+                }
             } else {
-                for (int j = 0; j < rows; ++j) row(base, j);
+                const int n = rows < KS_R ? rows : KS_R;
+                for (int j = 0; j < n; ++j) row(base, j);
             }
             __syncwarp();
             if (lane == 0) ks_arrive(&empty[stage]);
