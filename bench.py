@@ -331,7 +331,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--frames', type=int, default=256, help='frames per GPU per step')
-    ap.add_argument('--group', type=int, default=8, help='frames per K1/K2 launch inside the chain')
+    ap.add_argument('--group', type=int, default=32, help='frames per K1/K2 launch inside the chain')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-pool', type=int, default=32, help='pinned host frames cycled by the end-to-end leg')
     ap.add_argument('--e2e-steps', type=int, default=3)

@@ -51,7 +51,7 @@ struct imgcorr_ctx {
     LensConst lens{};
     double* lens_dev = nullptr;
     void* dump = nullptr;                     // scratch for stores of lanes that own no output pixel
-    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 1;
+    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 16;
     long long chain_groups_seen = 0;
     double prof_frames[2] = {0.0, 0.0};
     std::vector<cudaEvent_t> prof_ev[2];      // [kernel] start/stop pairs
@@ -381,6 +381,7 @@ static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, 
     c->launches += l;
     if (e == cudaErrorInvalidValue && l == 0)
         return fail(IMGCORR_ERR_INVALID, "unsupported dtype pair src=%d dst=%d", sdt, ddt);
+    if (e == cudaErrorNotSupported) return fail(IMGCORR_ERR_INVALID, "requested K2 variant is not eligible for this dtype / alignment");
     if (e != cudaSuccess) return cuda_fail(e, "K2 launch");
     return IMGCORR_OK;
 }

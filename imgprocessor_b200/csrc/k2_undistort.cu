@@ -14,6 +14,7 @@
 // A thread owns one output column and four rows of a 32x32 tile (consecutive lanes = consecutive
 // columns: coalesced stores, neighbouring gathers).  When P^-1 has no cross terms (what
 // getOptimalNewCameraMatrix always produces) x depends on the column only and is hoisted.
+#include <cuda.h>
 #include "imgcorr_kernels.cuh"
 
 namespace imgcorr {
@@ -181,6 +182,212 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Tiled variant (float32 sources — the chain): the source window of a 64x16 output tile is staged in shared memory
+// by ONE TMA box per frame, and the four neighbours are gathered from there.  The L1 path above spends ~8 L1
+// wavefronts per 32 pixels on the gather (unaligned, two rows) and is bound by them; shared memory serves the same
+// gather in ~4-5 conflict-free wavefronts, TMA moves whole lines, and the frames of a launch are double-buffered so
+// the box of frame f+1 lands while frame f is blended.
+//   * coordinates / weights / shared offsets of the tile's pixels are computed once (4 pixels per thread);
+//   * the exact bounding box of the tile's source window comes from a block-wide min/max (REDUX + shared atomics);
+//     box origin = (min ix rounded down to 4 columns — TMA's 16-byte rule —, min iy).  If the window does not fit the
+//     fixed 80x32 box (very strong distortion) the tile falls back to global gathers: correct for any map;
+//   * rim pixels (window touching the frame border) are redone from global memory with per-neighbour border handling.
+constexpr int KT_TW = 64, KT_TH = 16, KT_THREADS = 256, KT_PX = 4;
+constexpr int KT_BW = 80, KT_BH = 32;
+constexpr int KT_BOX_BYTES = KT_BW * KT_BH * 4;          // 10240
+#ifndef KT_NBUF_V
+#define KT_NBUF_V 4
+#endif
+#ifndef KT_MINB_V
+#define KT_MINB_V 4
+#endif
+constexpr int KT_NBUF = KT_NBUF_V;                       // frames of a launch in flight per tile
+constexpr int KT_SMEM = KT_NBUF * KT_BOX_BYTES + 128;
+
+__device__ __forceinline__ uint32_t kt_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <typename DstT, int MODE>
+__global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, K2Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = (uint64_t*)(smem + KT_NBUF * KT_BOX_BYTES);
+    int* red = (int*)(smem + KT_NBUF * KT_BOX_BYTES + 64);     // min ix, max ix, min iy, max iy
+    const int tid = threadIdx.x;
+    const int c = tid % KT_TW, r0 = tid / KT_TW;               // rows r0 + 4j
+    const int ox = blockIdx.x * KT_TW + c;
+    const int oy0 = blockIdx.y * KT_TH + r0;
+    const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
+    const int u = (ox < ow ? ox : ow - 1) + a.x0;
+    const float bval = (float)a.border;
+
+    if (tid == 0) {
+        for (int b = 0; b < KT_NBUF; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(kt_s32(&full[b])));
+        red[0] = 0x7fffffff; red[1] = -1; red[2] = 0x7fffffff; red[3] = -1;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    LensConst L = a.lens;
+    if (MODE == 2) {
+        const double2* lp = reinterpret_cast<const double2*>(a.lens_dev);
+        double2 q;
+        q = __ldg(lp + 0); L.k1 = q.x; L.k2 = q.y;
+        q = __ldg(lp + 1); L.k3 = q.x; L.p1 = q.y;
+        q = __ldg(lp + 2); L.p2 = q.x; L.p1x2 = q.y;
+        q = __ldg(lp + 3); L.p2x2 = q.x; L.fx = q.y;
+        q = __ldg(lp + 4); L.fy = q.x; L.cx = q.y;
+        q = __ldg(lp + 5); L.cy = q.x; L.ir[0] = q.y;
+        q = __ldg(lp + 6); L.ir[2] = q.x; L.ir[4] = q.y;
+        q = __ldg(lp + 7); L.ir[5] = q.x;
+    }
+    double xc = 0.0, xc2 = 0.0;
+    if (MODE == 2) {
+        xc = fma((double)u, L.ir[0], L.ir[2]);
+        xc2 = dmul(xc, xc);
+    }
+    int cix[KT_PX], ciy[KT_PX];
+    Weights<float> wt[KT_PX];
+    unsigned rim = 0, fast = 0;
+    int mnx = 0x7fffffff, mxx = -1, mny = 0x7fffffff, mxy = -1;
+#pragma unroll
+    for (int j = 0; j < KT_PX; ++j) {
+        const int oy = oy0 + j * (KT_THREADS / KT_TW);
+        const int v = (oy < oh ? oy : oh - 1) + a.y0;
+        float mx, my;
+        if (MODE == 2) {
+            const double y = fma((double)v, L.ir[4], L.ir[5]);
+            map_distort(L, xc, y, xc2, dmul(y, y), mx, my);
+        } else if (MODE == 1) {
+            undistort_map(L, u, v, mx, my);
+        } else {
+            mx = __ldg(a.mapx + v * W + u);
+            my = __ldg(a.mapy + v * W + u);
+        }
+        const FixedCoord fc = fixed_coord(mx, my);
+        cix[j] = fc.ix; ciy[j] = fc.iy;
+        wt[j].set(fc);
+        const bool live = ox < ow && oy < oh;
+        const bool inner = (unsigned)fc.ix < (unsigned)(W - 1) && (unsigned)fc.iy < (unsigned)(H - 1);
+        if (live && inner) {
+            fast |= 1u << j;
+            mnx = min(mnx, fc.ix); mxx = max(mxx, fc.ix); mny = min(mny, fc.iy); mxy = max(mxy, fc.iy);
+        } else if (live) {
+            rim |= 1u << j;
+        }
+    }
+    __syncthreads();                                   // red[] and the barriers are initialised
+    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
+    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
+    if ((tid & 31) == 0) { atomicMin(&red[0], mnx); atomicMax(&red[1], mxx); atomicMin(&red[2], mny); atomicMax(&red[3], mxy); }
+    __syncthreads();
+    const int bx = red[0] & ~3, by = red[2];
+    const bool any = red[1] >= 0;
+    const bool fits = any && (red[1] + 1 - bx) < KT_BW && (red[3] + 1 - by) < KT_BH;
+
+    DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
+    const int dstep = (KT_THREADS / KT_TW) * ow;
+    const int src_stride = H * W, dst_stride = oh * ow;
+    if (fits) {
+        int so[KT_PX];
+#pragma unroll
+        for (int j = 0; j < KT_PX; ++j) so[j] = (fast & (1u << j)) ? (ciy[j] - by) * KT_BW + (cix[j] - bx) : 0;
+        auto issue = [&](int f) {
+            const uint32_t bar = kt_s32(&full[f % KT_NBUF]);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(KT_BOX_BYTES) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                ::"r"(kt_s32(smem + (f % KT_NBUF) * KT_BOX_BYTES)), "l"(&tm_src), "r"(bar), "r"(bx), "r"(by), "r"(f) : "memory");
+        };
+        if (tid == 0) for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f);
+#pragma unroll 1
+        for (int f = 0; f < nf; ++f) {
+            const uint32_t bar = kt_s32(&full[f % KT_NBUF]);
+            const uint32_t parity = (f / KT_NBUF) & 1;
+            uint32_t done;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+            } while (!done);
+            const float* box = (const float*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j) {
+                const float* p = box + so[j];
+                const float r = blend_f32(p[0], p[1], p[KT_BW], p[KT_BW + 1], wt[j].w00, wt[j].w01, wt[j].w10, wt[j].w11);
+                if (fast & (1u << j)) dst[j * dstep] = (DstT)r;
+            }
+            dst += dst_stride;
+            __syncthreads();                           // everyone is done with this buffer
+            if (tid == 0 && f + KT_NBUF < nf) issue(f + KT_NBUF);
+        }
+    } else if (any) {
+        // the source window of this tile does not fit the staged box: gather from global memory
+        const float* src = (const float*)a.src;
+        for (int f = 0; f < nf; ++f) {
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j)
+                if (fast & (1u << j)) {
+                    const float* p = src + (ciy[j] * W + cix[j]);
+                    dst[j * dstep] = (DstT)blend_f32(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), wt[j].w00, wt[j].w01,
+                                                     wt[j].w10, wt[j].w11);
+                }
+            src += src_stride;
+            dst += dst_stride;
+        }
+    }
+    if (rim) {
+        const float* src = (const float*)a.src;
+        DstT* d2 = (DstT*)a.dst + (oy0 * ow + ox);
+        for (int f = 0; f < nf; ++f) {
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j)
+                if (rim & (1u << j)) d2[j * dstep] = remap_rim<float, DstT>(src, H, W, cix[j], ciy[j], wt[j], bval);
+            src += src_stride;
+            d2 += dst_stride;
+        }
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled_k2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled_k2 k2_encode_fn() {
+    static PFN_encodeTiled_k2 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_encodeTiled_k2)p;
+    }
+    return fn;
+}
+
+static bool k2_tiled_eligible(const K2Args& a, int src_dtype, int dst_dtype) {
+    if (src_dtype != DT_F32 || (dst_dtype != DT_F32 && dst_dtype != DT_F64)) return false;
+    if (a.W < 2 || a.H < 2) return false;
+    if (((size_t)a.W * 4) % 16 || ((uintptr_t)a.src) % 16) return false;
+    return k2_encode_fn() != nullptr;
+}
+
+template <typename DstT>
+static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
+    CUtensorMap tm;
+    cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_frames};
+    cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.W * a.H * 4};
+    cuuint32_t box[3] = {KT_BW, KT_BH, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if (k2_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(a.src), dims, strides, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return cudaErrorInvalidValue;
+    dim3 grid((a.ow + KT_TW - 1) / KT_TW, (a.oh + KT_TH - 1) / KT_TH);
+    if (a.mapx) k2_tiled_kernel<DstT, 0><<<grid, KT_THREADS, KT_SMEM, st>>>(tm, a);
+    else if (a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0) k2_tiled_kernel<DstT, 2><<<grid, KT_THREADS, KT_SMEM, st>>>(tm, a);
+    else k2_tiled_kernel<DstT, 1><<<grid, KT_THREADS, KT_SMEM, st>>>(tm, a);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) k2_write_maps_kernel(LensConst lens, float* mapx, float* mapy, int H, int W) {
     const int u = blockIdx.x * 32 + (threadIdx.x % 32);
     const int v = blockIdx.y * 8 + (threadIdx.x / 32);
@@ -203,13 +410,16 @@ static cudaError_t launch_t(const K2Args& a, cudaStream_t st) {
 }
 
 cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t st, int* launches) {
-    (void)variant;
     if (a.n_frames <= 0 || a.ow <= 0 || a.oh <= 0) return cudaSuccess;
     if (a.H > 32767 || a.W > 32767) return cudaErrorInvalidValue;      // OpenCV's remap itself is limited to short coordinates
     if (a.x0 < 0 || a.y0 < 0 || a.x0 + a.ow > a.W || a.y0 + a.oh > a.H) return cudaErrorInvalidValue;
     if ((a.mapx == nullptr) != (a.mapy == nullptr)) return cudaErrorInvalidValue;
     if (!a.mapx && !a.lens_dev) return cudaErrorInvalidValue;
+    // variant: 0 auto, 1 gathers through L1, 2 shared-memory staged tiles (float32 sources)
+    const bool tiled = variant != 1 && k2_tiled_eligible(a, src_dtype, dst_dtype);
+    if (variant == 2 && !tiled) return cudaErrorNotSupported;
     if (launches) ++*launches;
+    if (tiled) return dst_dtype == DT_F32 ? launch_tiled_t<float>(a, st) : launch_tiled_t<double>(a, st);
     if (src_dtype == DT_F32 && dst_dtype == DT_F32) return launch_t<float, float>(a, st);
     if (src_dtype == DT_F32 && dst_dtype == DT_F64) return launch_t<float, double>(a, st);
     if (src_dtype == DT_F64 && dst_dtype == DT_F64) return launch_t<double, double>(a, st);

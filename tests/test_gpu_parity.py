@@ -335,6 +335,40 @@ def test_remap_explicit_maps_vs_model(ip, dtype):
         assert np.array_equal(wide, models.remap_model(src, mapx, mapy, 0).astype(np.float64))
 
 
+@pytest.mark.parametrize('k2_variant', [1, 2])
+@pytest.mark.parametrize('lens_kind', ['moderate', 'strong'])
+def test_k2_variants_bit_identical(ip, k2_variant, lens_kind):
+    """K2 through L1 gathers (1) and through TMA-staged shared-memory tiles (2): same bits, several frames per launch,
+    roi window, float64 widening; the strong lens and the jittered explicit maps overflow the staged box -> fallback"""
+    H, W, n = 200, 328, 3
+    p = synth.lens_moderate(H, W) if lens_kind == 'moderate' else synth.lens_strong(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    mapx, mapy, P, roi = refpath.undistort_rectify_map(K, d, W, H)
+    e = _eng(ip, H, W)
+    e.set_lens(K, d, P)
+    e.set_option(ip.lib_mod.OPT_K2_VARIANT, k2_variant)
+    try:
+        frames = np.stack([synth.scene(H, W, 40 + i, np.float32) for i in range(n)])
+        mx, my = (m.cpu().numpy() for m in e.undistort_maps())
+        full = e.undistort(_dev(frames), border_value=3.5).cpu().numpy()
+        x, y, w, h = (int(v) for v in roi)
+        crop = e.undistort(_dev(frames), window=(x, y, w, h), out_dtype=torch.float64).cpu().numpy()
+        for i in range(n):
+            want = models.remap_model(frames[i], mx, my, 3.5)
+            assert np.array_equal(full[i], want)
+            want0 = models.remap_model(frames[i], mx, my, 0.0)
+            assert crop.dtype == np.float64 and np.array_equal(crop[i], want0[y:y + h, x:x + w].astype(np.float64))
+        rng = np.random.default_rng(5)
+        jx = np.arange(W, dtype=np.float32)[None, :] + rng.normal(0, 6, (H, W)).astype(np.float32)
+        jy = np.arange(H, dtype=np.float32)[:, None] + rng.normal(0, 6, (H, W)).astype(np.float32)
+        jx[0, :3] = [np.nan, -5.0, W + 3.0]
+        got = e.remap(_dev(frames), _dev(jx), _dev(jy), 1.25).cpu().numpy()
+        for i in range(n):
+            assert np.array_equal(got[i], models.remap_model(frames[i], jx, jy, 1.25))
+    finally:
+        e.set_option(ip.lib_mod.OPT_K2_VARIANT, 0)
+
+
 def test_undistort_multi_frame_and_window(ip):
     H, W, n = 125, 166, 4
     p = synth.lens_moderate(H, W)

@@ -13,6 +13,8 @@ n = 8
 src = torch.rand((n, H, W), dtype=torch.float32, device='cuda')
 out = torch.empty((n, H, W), dtype=torch.float32, device='cuda')
 res = []
+kv = int(os.environ.get('K2V', '0'))
+e.set_option(_lib.OPT_K2_VARIANT, kv)
 def t(fn, iters=24):
     for i in range(3): fn(i)
     torch.cuda.synchronize()
@@ -27,4 +29,4 @@ res.append('4 frames/launch: %.1f us/frame' % (t(lambda i: e.undistort(src[4 * (
 res.append('8 frames/launch: %.1f us/frame' % (t(lambda i: e.undistort(src, out=out), 6) / 8))
 mx, my = e.undistort_maps()
 res.append('explicit maps: %.1f us' % t(lambda i: e.remap(src[i % n], mx, my)))
-print(os.environ.get('IMGCORR_LIB', 'default').split('/')[-1], ' | '.join(res))
+print('k2 variant', kv, os.environ.get('IMGCORR_LIB', 'default').split('/')[-1], ' | '.join(res))
