@@ -311,7 +311,9 @@ def run_ours(args):
             'roofline': {'bound': 'hbm', 'kernel': 'K1 k1_stream_kernel (fused dark/flat/nan_to_num/3x3 median-threshold)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': args.k1_traffic,
                          'peak_source': peak_src, 'algorithmic_bytes_per_px': K1_BYTES_PER_PX,
-                         'us_per_frame': k1_us, 'frames_timed': k1_frames,
+                         'us_per_frame': k1_us, 'frames_timed': k1_frames, 'frames_per_launch': min(args.group, F),
+                         'launch_us': k1_us * min(args.group, F),
+                         'algorithmic_bytes_per_launch': K1_BYTES_PER_PX * H * W * min(args.group, F),
                          'k2': {'achieved': k2_achieved, 'frac': k2_achieved / peak, 'us_per_frame': k2_us,
                                 'algorithmic_bytes_per_px': K2_BYTES_PER_PX},
                          'chain_frac': (K1_BYTES_PER_PX + K2_BYTES_PER_PX) * H * W / ((k1_us + k2_us) * 1e-6) / 1e9 / peak
@@ -340,7 +342,9 @@ def main():
     args.k1_traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture
         with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
-            args.k1_traffic = float(json.load(f)['k1_dram_bytes_per_launch'])
+            t = json.load(f)
+        if int(t['frames_per_launch']) == args.group:          # the capture is of a launch of that many frames
+            args.k1_traffic = float(t['k1_dram_bytes_per_launch'])
     except Exception:
         pass
     if args.warmup < 3 and args.impl == 'ours':
