@@ -19,8 +19,8 @@
 // vertically adjacent windows; three sorted triples combine to the median of 9 (FMNMX3).
 // The kernel is instruction-issue bound, not DRAM bound (profiles/), so the structure is chosen to
 // minimise issued instructions per pixel.
-#include <cuda.h>
 #include "imgcorr_kernels.cuh"
+#include "imgcorr_tma.cuh"
 
 namespace imgcorr {
 
@@ -201,35 +201,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_generic_kernel(K1Args a, int ti
 // ------------------------------------------------------------------------------------------
 // TMA variant
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
-
 template <typename RawT, int KS, int TH, int NSTAGE>
 struct K1TmaSmem {
     static constexpr int HALO = KS / 2;
@@ -295,8 +266,7 @@ k1_tma_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant_
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&full[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -367,38 +337,6 @@ k1_tma_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant_
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode_fn() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
-    return fn;
-}
-
-static bool make_map(CUtensorMap* tm, CUtensorMapDataType dt, size_t esz, const void* ptr, int W, int H, int N,
-                     int boxw, int boxh) {
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(N > 0 ? N : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)W * esz, (cuuint64_t)W * H * esz};
-    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const int rank = N > 0 ? 3 : 2;
-    CUresult r = enc(tm, dt, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS;
-}
-
 bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (a.ksize != 3 && a.ksize != 5) return false;
     if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
@@ -411,7 +349,7 @@ bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (a.mask && ((uintptr_t)a.mask) % 2) return false;
     if (a.dark && ((uintptr_t)a.dark) % 16) return false;
     if (a.flat && ((uintptr_t)a.flat) % 16) return false;
-    return get_encode_fn() != nullptr;
+    return tensor_map_encoder() != nullptr;
 }
 
 template <typename RawT, typename OutT, int KS, int TH, int NSTAGE>
@@ -419,11 +357,11 @@ static cudaError_t launch_tma_t(const K1Args& a, CUtensorMapDataType rdt, int sm
     using S = K1TmaSmem<RawT, KS, TH, NSTAGE>;
     CUtensorMap tr, td, tf;
     const int boxh = S::LH;
-    if (!make_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, RawBox<RawT>::BOXW, boxh)) return cudaErrorInvalidValue;
+    if (!make_tensor_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, RawBox<RawT>::BOXW, boxh)) return cudaErrorInvalidValue;
     // dark / flat maps: encode the raw pointer as a placeholder when absent (never dereferenced)
-    if (!make_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, K1_BOXW, boxh) && a.dark)
+    if (!make_tensor_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, K1_BOXW, boxh) && a.dark)
         return cudaErrorInvalidValue;
-    if (!make_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K1_BOXW, boxh) && a.flat)
+    if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K1_BOXW, boxh) && a.flat)
         return cudaErrorInvalidValue;
     auto kern = k1_tma_kernel<RawT, OutT, KS, TH, NSTAGE>;
     static bool attr_set = false;

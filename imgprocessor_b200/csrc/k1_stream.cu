@@ -16,8 +16,8 @@
 //   * vertical 'reflect' needs no halo rows: the first / last row's sorted triple is used twice.
 //
 // Same arithmetic as the tile kernels (imgcorr_core.cuh) — results are bit-identical.
-#include <cuda.h>
 #include "imgcorr_kernels.cuh"
+#include "imgcorr_tma.cuh"
 
 namespace imgcorr {
 
@@ -51,37 +51,6 @@ template <typename RawT> struct StreamBox {
     static constexpr size_t bar_off = KS_NSTAGE * stage_bytes;
     static constexpr size_t total = bar_off + 2 * KS_NSTAGE * sizeof(uint64_t) + 64;
 };
-
-__device__ __forceinline__ uint32_t ks_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ks_bar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ks_s32(bar)), "r"(count));
-}
-__device__ __forceinline__ void ks_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ks_s32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ks_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ks_s32(bar)) : "memory");
-}
-__device__ __forceinline__ void ks_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(ks_s32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void ks_tma_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(ks_s32(dst)), "l"(tm), "r"(ks_s32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void ks_tma_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(ks_s32(dst)), "l"(tm), "r"(ks_s32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
 
 template <typename T> struct StreamRaw;
 template <> struct StreamRaw<uint8_t>  { static __device__ __forceinline__ void ld(uint8_t v, double& d, float& a)  { d = (double)(int)v; a = 0.0f; } };
@@ -146,10 +115,9 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 
     float* sconst = (float*)(smem + B::bar_off + 2 * KS_NSTAGE * sizeof(uint64_t));      // lo, hi, thr (double)
     if (threadIdx.x == 0) {
-        for (int s = 0; s < KS_NSTAGE; ++s) { ks_bar_init(&full[s], 1); ks_bar_init(&empty[s], KS_CW); }
+        for (int s = 0; s < KS_NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], KS_CW); }
         sconst[0] = a.pred.lo; sconst[1] = a.pred.hi; *(double*)(sconst + 2) = a.pred.thr;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
 
@@ -162,13 +130,13 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
             const UnitGeom u = ks_unit(unit, strips, segs, seg_rows, H, a.n_frames);
             for (int k = 0; k < u.nchunk; ++k, ++g) {
                 const int stage = g % KS_NSTAGE;
-                ks_wait(&empty[stage], ((g / KS_NSTAGE) & 1) ^ 1);
+                mbar_wait(&empty[stage], ((g / KS_NSTAGE) & 1) ^ 1);
                 uint8_t* base = smem + (size_t)stage * B::stage_bytes;
                 const int y = u.yl0 + k * KS_R;
-                ks_expect_tx(&full[stage], tx_bytes);
-                ks_tma_3d(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame);
-                if (has_dark) ks_tma_2d(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
-                if (has_flat) ks_tma_2d(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
+                mbar_expect_tx(&full[stage], tx_bytes);
+                tma_load_3d(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame);
+                if (has_dark) tma_load_2d(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
+                if (has_flat) tma_load_2d(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
             }
         }
         return;
@@ -244,7 +212,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 
         for (int k = 0; k < u.nchunk; ++k, ++g) {
             const int stage = g % KS_NSTAGE;
-            ks_wait(&full[stage], (g / KS_NSTAGE) & 1);
+            mbar_wait(&full[stage], (g / KS_NSTAGE) & 1);
             const uint8_t* base = smem + (size_t)stage * B::stage_bytes;
             if (k == 0) {
                 // vertical 'reflect' at the top (and a defined s0/s1 elsewhere): the first row's triple is used twice
@@ -293,7 +261,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                 for (int j = 0; j < n; ++j) row(base, j);
             }
             __syncwarp();
-            if (lane == 0) ks_arrive(&empty[stage]);
+            if (lane == 0) mbar_arrive(&empty[stage]);
         }
         if (u.ye == H) {
             // vertical 'reflect' at the bottom: output row H-1 sees (H-2, H-1, H-1)
@@ -304,38 +272,6 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------ host
-typedef CUresult (*PFN_encodeTiled_s)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled_s ks_encode_fn() {
-    static PFN_encodeTiled_s fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled_s)p;
-    }
-    return fn;
-}
-
-static bool ks_make_map(CUtensorMap* tm, CUtensorMapDataType dt, size_t esz, const void* ptr, int W, int H, int N,
-                        int boxw, int boxh) {
-    PFN_encodeTiled_s enc = ks_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(N > 0 ? N : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)W * esz, (cuuint64_t)W * H * esz};
-    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const int rank = N > 0 ? 3 : 2;
-    return enc(tm, dt, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (a.ksize != 3) return false;
     if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
@@ -347,7 +283,7 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (((uintptr_t)a.raw) % 16) return false;
     if (a.dark && ((uintptr_t)a.dark) % 16) return false;
     if (a.flat && ((uintptr_t)a.flat) % 16) return false;
-    return ks_encode_fn() != nullptr;
+    return tensor_map_encoder() != nullptr;
 }
 
 template <typename RawT, typename OutT>
@@ -370,10 +306,10 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     else { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 4; }
 
     CUtensorMap tr, td, tf;
-    if (!ks_make_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
-    if (!ks_make_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.dark)
+    if (!make_tensor_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
+    if (!make_tensor_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.dark)
         return cudaErrorInvalidValue;
-    if (!ks_make_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
+    if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
     static int per_sm[5] = {0, 0, 0, 0, 0};
     if (!per_sm[slot]) {

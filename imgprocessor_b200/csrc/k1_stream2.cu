@@ -21,8 +21,8 @@
 // Strip = 248 output columns (4 consumer warps x 62), staged box = 256 columns starting 8 columns left of
 // the strip (16-byte aligned for uint16 and float32 rows; strip k covers output columns 248k-7 .. 248k+240).
 // Same arithmetic as every other K1 variant (imgcorr_core.cuh): results are bit-identical.
-#include <cuda.h>
 #include "imgcorr_kernels.cuh"
+#include "imgcorr_tma.cuh"
 
 namespace imgcorr {
 
@@ -55,37 +55,6 @@ template <typename RawT, int R, int NSTAGE> struct Stream2Smem {
     static constexpr size_t const_off = bar_off + 2 * NSTAGE * sizeof(uint64_t);
     static constexpr size_t total = const_off + 64;
 };
-
-__device__ __forceinline__ uint32_t s2_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void s2_bar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2_s32(bar)), "r"(count));
-}
-__device__ __forceinline__ void s2_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2_s32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void s2_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2_s32(bar)) : "memory");
-}
-__device__ __forceinline__ void s2_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done) : "r"(s2_s32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void s2_tma_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(s2_s32(dst)), "l"(tm), "r"(s2_s32(bar)), "r"(x), "r"(y) : "memory");
-}
-__device__ __forceinline__ void s2_tma_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(s2_s32(dst)), "l"(tm), "r"(s2_s32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
-}
 
 // two adjacent raw samples of a row, as float64
 template <typename RawT> __device__ __forceinline__ void s2_load_pair(const RawT* row, int b0, double& v0, double& v1, float& a0, float& a1);
@@ -152,10 +121,9 @@ k1_stream2_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
     const int H = a.H, W = a.W;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { s2_bar_init(&full[s], 1); s2_bar_init(&empty[s], K2S_CW); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], K2S_CW); }
         sc->lo = a.pred.lo; sc->hi = a.pred.hi; sc->thr = a.pred.thr;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     __syncthreads();
 
@@ -168,13 +136,13 @@ k1_stream2_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
             const S2Unit u = s2_unit<R>(unit, strips, segs, seg_rows, H);
             for (int k = 0; k < u.nchunk; ++k, ++g) {
                 const int stage = g % NSTAGE;
-                s2_wait(&empty[stage], ((g / NSTAGE) & 1) ^ 1);
+                mbar_wait(&empty[stage], ((g / NSTAGE) & 1) ^ 1);
                 uint8_t* base = smem + (size_t)stage * S::stage_bytes;
                 const int y = u.yl0 + k * R;
-                s2_expect_tx(&full[stage], tx_bytes);
-                s2_tma_3d(base, &tm_raw, &full[stage], u.bx0, y, u.frame);
-                if (has_dark) s2_tma_2d(base + S::raw_bytes, &tm_dark, &full[stage], u.bx0, y);
-                if (has_flat) s2_tma_2d(base + S::raw_bytes + S::map_bytes, &tm_flat, &full[stage], u.bx0, y);
+                mbar_expect_tx(&full[stage], tx_bytes);
+                tma_load_3d(base, &tm_raw, &full[stage], u.bx0, y, u.frame);
+                if (has_dark) tma_load_2d(base + S::raw_bytes, &tm_dark, &full[stage], u.bx0, y);
+                if (has_flat) tma_load_2d(base + S::raw_bytes + S::map_bytes, &tm_flat, &full[stage], u.bx0, y);
             }
         }
         return;
@@ -260,7 +228,7 @@ k1_stream2_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
 
         for (int k = 0; k < u.nchunk; ++k, ++g) {
             const int stage = g % NSTAGE;
-            s2_wait(&full[stage], (g / NSTAGE) & 1);
+            mbar_wait(&full[stage], (g / NSTAGE) & 1);
             uint8_t* base = smem + (size_t)stage * S::stage_bytes;
             const int rows = u.n_in - k * R < R ? u.n_in - k * R : R;
             patch(base, rows);
@@ -299,7 +267,7 @@ k1_stream2_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
                 }
             }
             __syncwarp();
-            if (lane == 0) s2_arrive(&empty[stage]);
+            if (lane == 0) mbar_arrive(&empty[stage]);
         }
         if (u.ye == H) {
             // vertical 'reflect' at the bottom: output row H-1 sees (H-2, H-1, H-1)
@@ -310,38 +278,6 @@ k1_stream2_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
 }
 
 // ------------------------------------------------------------------------------------------ host
-typedef CUresult (*PFN_encodeTiled_s2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled_s2 s2_encode_fn() {
-    static PFN_encodeTiled_s2 fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled_s2)p;
-    }
-    return fn;
-}
-
-static bool s2_make_map(CUtensorMap* tm, CUtensorMapDataType dt, size_t esz, const void* ptr, int W, int H, int N,
-                        int boxw, int boxh) {
-    PFN_encodeTiled_s2 enc = s2_encode_fn();
-    if (!enc) return false;
-    cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(N > 0 ? N : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)W * esz, (cuuint64_t)W * H * esz};
-    cuuint32_t box[3] = {(cuuint32_t)boxw, (cuuint32_t)boxh, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    const int rank = N > 0 ? 3 : 2;
-    return enc(tm, dt, rank, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
 // which specialisation serves this call, or -1
 static int s2_config(const K1Args& a, int raw_dtype) {
     const int f = a.pw.flags;
@@ -370,7 +306,7 @@ bool k1_stream2_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (a.dark && ((uintptr_t)a.dark) % 16) return false;
     if (a.flat && ((uintptr_t)a.flat) % 16) return false;
     if (s2_config(a, raw_dtype) < 0) return false;
-    return s2_encode_fn() != nullptr;
+    return tensor_map_encoder() != nullptr;
 }
 
 template <typename RawT, typename OutT, int CFG, int R, int NSTAGE>
@@ -379,10 +315,10 @@ static cudaError_t launch_s2_cfg(const K1Args& a0, CUtensorMapDataType rdt, int 
     K1Args a = a0;
     if (CFG & S2_FLAT) a.flat = a.flat_nz;          // zero-free copy: division is unconditional
     CUtensorMap tr, td, tf;
-    if (!s2_make_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, K2S_BOXW, R)) return cudaErrorInvalidValue;
-    if (!s2_make_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, K2S_BOXW, R) && a.dark)
+    if (!make_tensor_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, K2S_BOXW, R)) return cudaErrorInvalidValue;
+    if (!make_tensor_map(&td, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.dark ? (const void*)a.dark : a.raw, a.W, a.H, 0, K2S_BOXW, R) && a.dark)
         return cudaErrorInvalidValue;
-    if (!s2_make_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K2S_BOXW, R) && a.flat)
+    if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K2S_BOXW, R) && a.flat)
         return cudaErrorInvalidValue;
     auto kern = k1_stream2_kernel<RawT, OutT, CFG, R, NSTAGE>;
     static int per_sm = 0;

@@ -14,8 +14,8 @@
 // A thread owns one output column and four rows of a 32x32 tile (consecutive lanes = consecutive
 // columns: coalesced stores, neighbouring gathers).  When P^-1 has no cross terms (what
 // getOptimalNewCameraMatrix always produces) x depends on the column only and is hoisted.
-#include <cuda.h>
 #include "imgcorr_kernels.cuh"
+#include "imgcorr_tma.cuh"
 
 namespace imgcorr {
 
@@ -205,7 +205,6 @@ constexpr int KT_BOX_BYTES = KT_BW * KT_BH * 4;          // 10240
 constexpr int KT_NBUF = KT_NBUF_V;                       // frames of a launch in flight per tile
 constexpr int KT_SMEM = KT_NBUF * KT_BOX_BYTES + 128;
 
-__device__ __forceinline__ uint32_t kt_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <typename DstT, int MODE>
 __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, K2Args a) {
@@ -221,10 +220,9 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
     const float bval = (float)a.border;
 
     if (tid == 0) {
-        for (int b = 0; b < KT_NBUF; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(kt_s32(&full[b])));
+        for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
         red[0] = 0x7fffffff; red[1] = -1; red[2] = 0x7fffffff; red[3] = -1;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_init_fence();
     }
     LensConst L = a.lens;
     if (MODE == 2) {
@@ -291,22 +289,14 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
 #pragma unroll
         for (int j = 0; j < KT_PX; ++j) so[j] = (fast & (1u << j)) ? (ciy[j] - by) * KT_BW + (cix[j] - bx) : 0;
         auto issue = [&](int f) {
-            const uint32_t bar = kt_s32(&full[f % KT_NBUF]);
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(KT_BOX_BYTES) : "memory");
-            asm volatile(
-                "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                ::"r"(kt_s32(smem + (f % KT_NBUF) * KT_BOX_BYTES)), "l"(&tm_src), "r"(bar), "r"(bx), "r"(by), "r"(f) : "memory");
+            uint64_t* bar = &full[f % KT_NBUF];
+            mbar_expect_tx(bar, KT_BOX_BYTES);
+            tma_load_3d(smem + (f % KT_NBUF) * KT_BOX_BYTES, &tm_src, bar, bx, by, f);
         };
         if (tid == 0) for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f);
 #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
-            const uint32_t bar = kt_s32(&full[f % KT_NBUF]);
-            const uint32_t parity = (f / KT_NBUF) & 1;
-            uint32_t done;
-            do {
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                             : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-            } while (!done);
+            mbar_wait(&full[f % KT_NBUF], (f / KT_NBUF) & 1);
             const float* box = (const float*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
 #pragma unroll
             for (int j = 0; j < KT_PX; ++j) {
@@ -346,41 +336,17 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
     }
 }
 
-typedef CUresult (*PFN_encodeTiled_k2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                       const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                       CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static PFN_encodeTiled_k2 k2_encode_fn() {
-    static PFN_encodeTiled_k2 fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled_k2)p;
-    }
-    return fn;
-}
-
 static bool k2_tiled_eligible(const K2Args& a, int src_dtype, int dst_dtype) {
     if (src_dtype != DT_F32 || (dst_dtype != DT_F32 && dst_dtype != DT_F64)) return false;
     if (a.W < 2 || a.H < 2) return false;
     if (((size_t)a.W * 4) % 16 || ((uintptr_t)a.src) % 16) return false;
-    return k2_encode_fn() != nullptr;
+    return tensor_map_encoder() != nullptr;
 }
 
 template <typename DstT>
 static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
     CUtensorMap tm;
-    cuuint64_t dims[3] = {(cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.n_frames};
-    cuuint64_t strides[2] = {(cuuint64_t)a.W * 4, (cuuint64_t)a.W * a.H * 4};
-    cuuint32_t box[3] = {KT_BW, KT_BH, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    if (k2_encode_fn()(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(a.src), dims, strides, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return cudaErrorInvalidValue;
+    if (!make_tensor_map(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.src, a.W, a.H, a.n_frames, KT_BW, KT_BH)) return cudaErrorInvalidValue;
     dim3 grid((a.ow + KT_TW - 1) / KT_TW, (a.oh + KT_TH - 1) / KT_TH);
     if (a.mapx) k2_tiled_kernel<DstT, 0><<<grid, KT_THREADS, KT_SMEM, st>>>(tm, a);
     else if (a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0) k2_tiled_kernel<DstT, 2><<<grid, KT_THREADS, KT_SMEM, st>>>(tm, a);

@@ -35,13 +35,14 @@ def main():
     ap.add_argument('--iters', type=int, default=48)
     ap.add_argument('--dtype', default='uint16')
     ap.add_argument('--ksize', type=int, default=3)
+    ap.add_argument('--lens', default='moderate')
     a = ap.parse_args()
     H, W, n = a.H, a.W, a.frames
     dev = torch.device('cuda', 0)
     e = engine.Engine(H, W, 0)
     e.set_dark(synth.dark_map(H, W))
     e.set_flat(synth.flat_map(H, W))
-    p = synth.lens_moderate(H, W)
+    p = synth.lens_moderate(H, W) if a.lens == 'moderate' else synth.lens_strong(H, W)
     import cv2
     K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
     P, roi = cv2.getOptimalNewCameraMatrix(K, d, (W, H), 1, (W, H))
@@ -65,7 +66,7 @@ def main():
             rep(nm, med, best, rb + 12)
         except Exception as ex:
             print(nm, 'failed:', ex)
-    for seg in (48, 96, 144, 256, 512):
+    for seg in ():
         e.set_option(_lib.OPT_K1_VARIANT, 4)
         e.set_option(_lib.OPT_K1_SEG_ROWS, seg)
         try:
