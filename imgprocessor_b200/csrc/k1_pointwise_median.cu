@@ -141,23 +141,39 @@ __device__ __forceinline__ void median_phase(const CT* __restrict__ xs, const K1
         } else {
             for (int j = 0; j < nrows; ++j) step(j);
         }
-    } else {   // KS == 5: rows r .. r+4 of xs, columns c-2 .. c+3
-        for (int j = 0; j < nrows; ++j) {
-            const CT* p = xs + (size_t)(r0 + j) * K1_BOXW + (K1_XOFF + c - 2);
-            CT w0[25], w1[25];
+    } else {   // KS == 5
+        // one column at a time: walk down the rows keeping the last five SORTED horizontal quintuples in registers
+        // (each is sorted once and used by five windows); the loop is fully unrolled so the ring index is static.
 #pragma unroll
-            for (int dy = 0; dy < 5; ++dy) {
-                const Pair<CT> q0 = *reinterpret_cast<const Pair<CT>*>(p + dy * K1_BOXW);
-                const Pair<CT> q1 = *reinterpret_cast<const Pair<CT>*>(p + dy * K1_BOXW + 2);
-                const Pair<CT> q2 = *reinterpret_cast<const Pair<CT>*>(p + dy * K1_BOXW + 4);
-                w0[dy * 5 + 0] = q0.x; w0[dy * 5 + 1] = q0.y; w0[dy * 5 + 2] = q1.x; w0[dy * 5 + 3] = q1.y; w0[dy * 5 + 4] = q2.x;
-                w1[dy * 5 + 0] = q0.y; w1[dy * 5 + 1] = q1.x; w1[dy * 5 + 2] = q1.y; w1[dy * 5 + 3] = q2.x; w1[dy * 5 + 4] = q2.y;
+        for (int cc = 0; cc < 2; ++cc) {
+            if (cc == 1 && !two) break;
+            const CT* p = xs + (size_t)r0 * K1_BOXW + (K1_XOFF + c + cc - 2);       // xs row r0 = window row 0 of output r0
+            CT q[5][5];
+            CT ctr[5];
+#pragma unroll
+            for (int j = 0; j < P + 4; ++j) {
+                CT* row = q[j % 5];
+#pragma unroll
+                for (int dx = 0; dx < 5; ++dx) row[dx] = p[dx];
+                ctr[j % 5] = row[2];
+                sort5(row);
+                p += K1_BOXW;
+                if (j >= 4) {
+                    const int o = j - 4;                                       // output row inside this thread's run
+                    if (o < nrows) {
+                        CT w[25];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k)
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) w[5 * k + i] = q[(j - 4 + k) % 5][i];
+                        const CT med = median25_sorted_rows(w);
+                        const CT centre = ctr[(j - 2) % 5];
+                        const bool rep = predicate(centre, med, pred);
+                        out[(size_t)o * W + cc] = to_out<OutT, CT>(rep ? med : centre);
+                        if (mask) mask[(size_t)o * W + cc] = rep ? 1 : 0;
+                    }
+                }
             }
-            const CT c0 = w0[12], c1 = w1[12];
-            const CT m0 = median25(w0), m1 = median25(w1);
-            const bool rep0 = predicate(c0, m0, pred), rep1 = predicate(c1, m1, pred);
-            store_pair<OutT, VEC>(out + (size_t)j * W, to_out<OutT, CT>(rep0 ? m0 : c0), to_out<OutT, CT>(rep1 ? m1 : c1), two);
-            if (mask) store_pair<uint8_t, VEC>(mask + (size_t)j * W, (uint8_t)rep0, (uint8_t)rep1, two);
         }
     }
 }
@@ -232,7 +248,7 @@ template <> __device__ __forceinline__ void load_raw4<float>(const float* row, i
 }
 
 template <typename RawT, typename OutT, int KS, int TH, int NSTAGE>
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, KS == 5 ? 3 : 1)
 k1_tma_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_dark,
               const __grid_constant__ CUtensorMap tm_flat, K1Args a, int tiles_x, int tiles_y, int total_tiles) {
     using CT = float;
@@ -421,8 +437,7 @@ static cudaError_t dispatch_ks(const K1Args& a, bool tma, CUtensorMapDataType rd
     if (a.ksize == 5) {
         if constexpr (sizeof(RawT) <= 4 && sizeof(OutT) <= 4)
             if (tma) {
-                if constexpr (sizeof(RawT) <= 2) return launch_tma_t<RawT, OutT, 5, 32, 2>(a, rdt, sm_count, st);
-                else return launch_tma_t<RawT, OutT, 5, 16, 2>(a, rdt, sm_count, st);
+                return launch_tma_t<RawT, OutT, 5, 16, 2>(a, rdt, sm_count, st);      // 5x5 is register-heavy: small tiles, 3 CTAs / SM
             }
         return launch_generic_t<RawT, OutT, 5, 32>(a, st);
     }

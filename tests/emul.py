@@ -9,6 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'host_emul', 'emul.cpp')
 CORE = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_core.cuh')
+NET = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'median25_net.inc')
 OUT = os.path.join(HERE, '_build', 'libimgcorr_emul.so')
 _DT = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
 _lib = None
@@ -18,7 +19,7 @@ def lib():
     global _lib
     if _lib is None:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE)):
+        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NET)):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
                                    '-fvisibility=hidden', '-o', OUT, SRC, '-lm'])
         _lib = ctypes.CDLL(OUT)

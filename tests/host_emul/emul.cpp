@@ -51,9 +51,11 @@ static void k1_typed(const void* raw, int raw_dtype, const float* dark, const fl
                 if (rep) res = med;
             } else if (ksize == 5) {
                 CT w[25];
-                for (int dy = 0; dy < 5; ++dy)
+                for (int dy = 0; dy < 5; ++dy) {
                     for (int dx = 0; dx < 5; ++dx) w[dy * 5 + dx] = at(y + dy - 2, xx + dx - 2);
-                CT med = median25(w);
+                    sort5(w + dy * 5);
+                }
+                CT med = median25_sorted_rows(w);
                 rep = predicate(v, med, pc);
                 if (rep) res = med;
             }
