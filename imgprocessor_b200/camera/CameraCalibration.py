@@ -362,10 +362,15 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         self._checkShape(image)
         self.last_light_spectrum = light_spectrum
         H, W = image.shape
-        raw = image if image.dtype.type in (np.uint8, np.uint16, np.float32) else image.astype(np.float32)
+        big_endian = image.dtype.kind == 'u' and image.dtype.itemsize == 2 and image.dtype.byteorder == '>'
+        if big_endian:
+            raw = image.view(image.dtype.newbyteorder('<'))      # reader.RAW frames: same bytes, K1 swaps in its load
+        else:
+            raw = image if image.dtype.type in (np.uint8, np.uint16, np.float32) and image.dtype.isnative \
+                else image.astype(np.float32)
         eng = _engine.get_engine(H, W)
         flags = self._configure_engine(eng, (H, W), bgImages, exposure_time, light_spectrum, date)
-        self._last = (raw, flags)
+        self._last = (raw if not big_endian else image.astype(np.uint16), flags)
         if threshold > 0:
             print('... remove artefacts')
             flags |= _lib.DO_NAN_TO_NUM
@@ -392,8 +397,9 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         window = None
         if lens and not keep_size:
             window = tuple(int(v) for v in lens.roi)
-        out = eng.correct_batch(dev, threshold=threshold if threshold > 0 else 0.0, ksize=3, flags=flags,
-                                use_lens=bool(lens), window=window, out_dtype=tt.float64)
+        with eng.ingest(big_endian, 0):
+            out = eng.correct_batch(dev, threshold=threshold if threshold > 0 else 0.0, ksize=3, flags=flags,
+                                    use_lens=bool(lens), window=window, out_dtype=tt.float64)
         result = out.cpu().numpy()
         print('DONE')
         return result
@@ -455,7 +461,8 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         if is_tensor:
             return eng.correct_batch(frames, threshold=thr, ksize=3, flags=flags, use_lens=bool(lens), window=window,
                                      out_dtype=out_dtype or tt.float32, out=out)
-        if frames.dtype.type not in (np.uint8, np.uint16, np.float32):
+        be = frames.dtype.kind == 'u' and frames.dtype.itemsize == 2 and frames.dtype.byteorder == '>'
+        if not be and (frames.dtype.type not in (np.uint8, np.uint16, np.float32) or not frames.dtype.isnative):
             frames = frames.astype(np.float32)
         return eng.correct_host(frames, out=out, threshold=thr, ksize=3, flags=flags, use_lens=bool(lens),
                                 window=window, out_dtype=out_dtype or np.float32)

@@ -51,6 +51,8 @@ struct imgcorr_ctx {
     LensConst lens{};
     double* lens_dev = nullptr;
     void* dump = nullptr;                     // scratch for stores of lanes that own no output pixel
+    int raw_big_endian = 0;
+    long long raw_gap = 0;
     int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 16;
     long long chain_groups_seen = 0;
     double prof_frames[2] = {0.0, 0.0};
@@ -167,6 +169,13 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
         case IMGCORR_OPT_CHAIN_GROUP:
             if (value < 1 || value > 64) return fail(IMGCORR_ERR_INVALID, "chain group %d not in [1,64]", value);
             c->chain_group = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_RAW_BIG_ENDIAN:
+            c->raw_big_endian = value ? 1 : 0;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_RAW_FRAME_GAP:
+            if (value < 0) return fail(IMGCORR_ERR_INVALID, "frame gap %d", value);
+            c->raw_gap = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K1_SEG_ROWS:
             if (value < 0) return fail(IMGCORR_ERR_INVALID, "seg rows %d", value);
@@ -322,6 +331,11 @@ static int fill_k1(imgcorr_ctx* c, K1Args& a, const void* raw, int raw_dtype, vo
     a = K1Args{};
     a.raw = raw; a.out = out; a.mask = ksize ? mask : nullptr;
     a.H = c->H; a.W = c->W; a.n_frames = n; a.ksize = ksize;
+    a.raw_swap = (c->raw_big_endian && raw_dtype == DT_U16) ? 1 : 0;
+    a.raw_gap = c->raw_gap;
+    if (c->raw_big_endian && raw_dtype != DT_U16 && raw_dtype != DT_U8)
+        return fail(IMGCORR_ERR_INVALID, "big-endian ingest is implemented for uint16 frames");
+    if (c->raw_gap % (long long)dtype_size(raw_dtype)) return fail(IMGCORR_ERR_INVALID, "frame gap must be a multiple of the sample size");
     int f = 0;
     if ((flags & IMGCORR_DO_DARK) && c->dark) {
         f |= FLAG_DARK; a.dark = c->dark;
@@ -419,7 +433,7 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
     if (out_dtype != DT_F32 && out_dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "out_dtype must be F32 or F64");
     if (raw_dtype == DT_F64) return fail(IMGCORR_ERR_INVALID, "float64 frames: convert to float32 first (the chain computes in float32)");
     const size_t npx = (size_t)c->H * c->W;
-    const size_t raw_stride = npx * dtype_size(raw_dtype);
+    const size_t raw_stride = npx * dtype_size(raw_dtype) + (size_t)c->raw_gap;
     if (!lens) {
         if (x0 != 0 || y0 != 0 || ow != c->W || oh != c->H)
             return fail(IMGCORR_ERR_INVALID, "output window without a lens");
@@ -515,6 +529,7 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
     if (!raw_host || !out_host) return fail(IMGCORR_ERR_INVALID, "null image pointer");
     if (n_frames < 0) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n_frames);
     if (raw_dtype < DT_U8 || raw_dtype > DT_F32) return fail(IMGCORR_ERR_INVALID, "raw_dtype %d (U8, U16 or F32)", raw_dtype);
+    if (c->raw_gap) return fail(IMGCORR_ERR_INVALID, "IMGCORR_OPT_RAW_FRAME_GAP is not available for host frames (pass the pixel blocks)");
     if (out_dtype != DT_F32 && out_dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "out_dtype must be F32 or F64");
     const bool lens = use_lens && c->has_lens;
     if (!lens) { x0 = 0; y0 = 0; ow = c->W; oh = c->H; }

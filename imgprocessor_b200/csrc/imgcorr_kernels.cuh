@@ -20,6 +20,8 @@ struct K1Args {
     void* out;              // [n_frames][H][W] of out dtype
     uint8_t* mask;          // [n_frames][H][W] or null
     int H, W, n_frames;
+    int raw_swap;           // raw samples are big-endian uint16 (reader/RAW.py default): bytes swapped in the load
+    long long raw_gap;      // bytes between the end of one raw frame and the start of the next (reader/elbin.py: 20-byte headers)
     int ksize;              // 0 (pointwise only), 3, 5
     int maps_finite;        // dark / flat hold no NaN / inf (checked once at upload)
     const float* flat_nz;   // copy of flat with zeros replaced by 1.0 (unconditional division), or null

@@ -54,6 +54,16 @@ template <> __device__ __forceinline__ uint8_t  to_out<uint8_t, float>(float v) 
 
 template <typename T> struct alignas(2 * sizeof(T)) Pair { T x, y; };
 
+// ingest formats: big-endian uint16 samples (reader/RAW.py:19-20) and frames separated by small
+// headers (reader/elbin.py:23-32) are consumed as stored — byte swap in the load, frame stride with a gap
+template <typename RawT> __device__ __forceinline__ RawT raw_fix(RawT v, int) { return v; }
+template <> __device__ __forceinline__ uint16_t raw_fix<uint16_t>(uint16_t v, int swap) {
+    return swap ? (uint16_t)__byte_perm((unsigned)v, 0u, 0x0001) : v;
+}
+template <typename RawT> __device__ __forceinline__ const RawT* raw_frame(const K1Args& a, int frame) {
+    return (const RawT*)((const char*)a.raw + (size_t)frame * ((size_t)a.H * a.W * sizeof(RawT) + (size_t)a.raw_gap));
+}
+
 // ------------------------------------------------------------------------------------------
 // pointwise only (ksize == 0): pure streaming kernel; frames in grid.y, no per-pixel modulo
 // ------------------------------------------------------------------------------------------
@@ -61,14 +71,15 @@ template <typename RawT, typename OutT>
 __global__ void __launch_bounds__(256) k1_pointwise_kernel(K1Args a) {
     using CT = typename RawIO<RawT>::CT;
     const size_t npx = (size_t)a.H * a.W;
-    const RawT* raw = (const RawT*)a.raw + (size_t)blockIdx.y * npx;
+    const RawT* raw = raw_frame<RawT>(a, blockIdx.y);
     OutT* out = (OutT*)a.out + (size_t)blockIdx.y * npx;
     const PointwiseConst pw = a.pw;
+    const int swap = a.raw_swap;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += (size_t)gridDim.x * blockDim.x) {
         float d = a.dark ? __ldg(a.dark + p) : 0.0f;
         float s = a.ascent ? __ldg(a.ascent + p) : 0.0f;
         float f = a.flat ? __ldg(a.flat + p) : 0.0f;
-        out[p] = to_out<OutT, CT>(pointwise<CT>(pw, RawIO<RawT>::ld(__ldg(raw + p)), d, s, f));
+        out[p] = to_out<OutT, CT>(pointwise<CT>(pw, RawIO<RawT>::ld(raw_fix<RawT>(__ldg(raw + p), swap)), d, s, f));
     }
 }
 
@@ -194,8 +205,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_generic_kernel(K1Args a, int ti
     const int tyi = t % tiles_y;
     const int frame = t / tiles_y;
     const int tx0 = txi * K1_TW, ty0 = tyi * TH;
-    const RawT* raw = (const RawT*)a.raw + (size_t)frame * a.H * a.W;
+    const RawT* raw = raw_frame<RawT>(a, frame);
     const PointwiseConst pw = a.pw;
+    const int swap = a.raw_swap;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
     for (int ly = warp; ly < LH; ly += K1_THREADS / 32) {
@@ -206,7 +218,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_generic_kernel(K1Args a, int ti
             float d = a.dark ? __ldg(a.dark + g) : 0.0f;
             float s = a.ascent ? __ldg(a.ascent + g) : 0.0f;
             float f = a.flat ? __ldg(a.flat + g) : 0.0f;
-            xrow[lx] = pointwise<CT>(pw, RawIO<RawT>::ld(__ldg(raw + g)), d, s, f);
+            xrow[lx] = pointwise<CT>(pw, RawIO<RawT>::ld(raw_fix<RawT>(__ldg(raw + g), swap)), d, s, f);
         }
     }
     __syncthreads();
@@ -358,6 +370,7 @@ bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
     if (out_dtype != DT_F32 && !(raw_dtype == DT_U16 && out_dtype == DT_U16) && !(raw_dtype == DT_U8 && out_dtype == DT_U8)) return false;
     if (a.pw.flags & FLAG_DARK_LINEAR) return false;
+    if (a.raw_swap || a.raw_gap) return false;
     const size_t esz = dtype_size(raw_dtype);
     if (((size_t)a.W * esz) % 16 || ((size_t)a.W * 4) % 16) return false;
     if (((size_t)a.H * a.W * esz) % 16) return false;
@@ -416,7 +429,7 @@ static cudaError_t launch_pointwise_t(const K1Args& a, int sm_count, cudaStream_
     for (int f0 = 0; f0 < a.n_frames; f0 += 65535) {
         K1Args b = a;
         const int nf = a.n_frames - f0 < 65535 ? a.n_frames - f0 : 65535;
-        b.raw = (const char*)a.raw + (size_t)f0 * npx * sizeof(RawT);
+        b.raw = (const char*)a.raw + (size_t)f0 * (npx * sizeof(RawT) + (size_t)a.raw_gap);
         b.out = (char*)a.out + (size_t)f0 * npx * sizeof(OutT);
         k1_pointwise_kernel<RawT, OutT><<<dim3((unsigned)bx, (unsigned)nf), 256, 0, st>>>(b);
     }

@@ -92,7 +92,8 @@ __device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int 
 
 // CFG >= 0 bakes the per-launch switches into the instruction stream (the kernel is issue bound: every
 // per-row flag test costs); CFG < 0 reads them from the arguments.
-enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32, KS_NZ = 64 };
+enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32, KS_NZ = 64, KS_SWAP = 128 };
+// KS_SWAP: big-endian uint16 samples (reader/RAW.py default) — one PRMT per pixel after the shared-memory load
 // KS_NZ: a.flat is the zero-free copy (zeros replaced by 1.0) -> unconditional division
 // KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
 
@@ -109,6 +110,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     const bool has_flat = CFG >= 0 ? (CFG & KS_FLAT) != 0 : a.flat != nullptr;
     const bool has_mask = CFG >= 0 ? (CFG & KS_MASK) != 0 : a.mask != nullptr;
     const bool check = CFG >= 0 ? (CFG & KS_CHECK) != 0 : true;
+    const bool swap = CFG >= 0 ? (CFG & KS_SWAP) != 0 : a.raw_swap != 0;
     const int flags = CFG >= 0 ? ((CFG & KS_DARK ? FLAG_DARK : 0) | (CFG & KS_FLAT ? FLAG_FLAT : 0) | (CFG & KS_N2N ? FLAG_NAN_TO_NUM : 0))
                                : a.pw.flags;
     const int H = a.H, W = a.W;
@@ -170,7 +172,8 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
         int i = 0;
 
         auto pixel = [&](const uint8_t* base, int j) -> float {
-            const RawT rv = ((const RawT*)base)[j * B::BOXW + rcol];
+            RawT rv = ((const RawT*)base)[j * B::BOXW + rcol];
+            if (sizeof(RawT) == 2 && swap) rv = (RawT)__byte_perm((unsigned)rv, 0u, 0x0001);
             const float d = has_dark ? ((const float*)(base + B::raw_bytes))[j * KS_MAPW + mcol] : 0.0f;
             const float f = has_flat ? ((const float*)(base + B::raw_bytes + B::map_bytes))[j * KS_MAPW + mcol] : 0.0f;
             double rd; float ra;
@@ -277,6 +280,7 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
     if (out_dtype != DT_F32 && !(raw_dtype == DT_U16 && out_dtype == DT_U16) && !(raw_dtype == DT_U8 && out_dtype == DT_U8)) return false;
     if (a.pw.flags & FLAG_DARK_LINEAR) return false;
+    if (a.raw_gap) return false;
     const size_t esz = dtype_size(raw_dtype);
     if (((size_t)a.W * esz) % 16 || ((size_t)a.W * 4) % 16) return false;
     if (((size_t)a.H * a.W * esz) % 16) return false;
@@ -299,7 +303,12 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
     int slot;
     if (chain) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
-    if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ>; slot = 0; }
+    if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
+        kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP>
+                             : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP>;
+        slot = a.no_overflow ? 5 : 6;
+    } else if (a.raw_swap) { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 4; if (chain) a.flat = a_in.flat; }
+    else if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ>; slot = 0; }
     else if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ>; slot = 1; }
     else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK>; slot = 2; }
     else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK>; slot = 3; }
@@ -311,7 +320,7 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
         return cudaErrorInvalidValue;
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
-    static int per_sm[5] = {0, 0, 0, 0, 0};
+    static int per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
     if (!per_sm[slot]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
         if (e != cudaSuccess) return e;

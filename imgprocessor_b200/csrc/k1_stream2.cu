@@ -299,6 +299,7 @@ bool k1_stream2_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     if (raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
     if (out_dtype != DT_F32 && !(raw_dtype == DT_U16 && out_dtype == DT_U16)) return false;
     if (a.pw.flags & FLAG_DARK_LINEAR) return false;
+    if (a.raw_swap || a.raw_gap) return false;
     const size_t esz = dtype_size(raw_dtype);
     if (((size_t)a.W * esz) % 16 || ((size_t)a.W * 4) % 16) return false;
     if (((size_t)a.H * a.W * esz) % 16) return false;

@@ -156,6 +156,53 @@ class Engine(object):
         x, y, w, h = (int(v) for v in window)
         return x, y, w, h
 
+    class _Ingest(object):
+        """context manager: raw frames of the enclosed calls are big-endian uint16 and / or separated by `gap` bytes"""
+
+        def __init__(self, eng, big_endian, gap):
+            self.eng, self.be, self.gap = eng, bool(big_endian), int(gap)
+
+        def __enter__(self):
+            if self.be:
+                self.eng.set_option(_lib.OPT_RAW_BIG_ENDIAN, 1)
+            if self.gap:
+                self.eng.set_option(_lib.OPT_RAW_FRAME_GAP, self.gap)
+
+        def __exit__(self, *a):
+            if self.be:
+                self.eng.set_option(_lib.OPT_RAW_BIG_ENDIAN, 0)
+            if self.gap:
+                self.eng.set_option(_lib.OPT_RAW_FRAME_GAP, 0)
+
+    def ingest(self, big_endian=False, gap=0):
+        return Engine._Ingest(self, big_endian, gap)
+
+    def correct_file_bytes(self, buf, offset, n_frames, gap=0, big_endian=False, dtype=None, **kw):
+        """The chain on frames as they sit in a file image: ``buf`` is a uint8 CUDA tensor holding the file bytes,
+        the first frame's pixels start at byte ``offset`` and consecutive frames are ``gap`` bytes apart
+        (reader/elbin.py: 20-byte per-frame headers; reader/RAW.py: dense, big-endian by default).  No host-side
+        byte swap or de-interleave: K1 does both in its load.  kw as correct_batch."""
+        tt = torch()
+        dtype = dtype or tt.uint16
+        esz = {tt.uint8: 1, tt.uint16: 2, tt.float32: 4}[dtype]
+        need = offset + n_frames * self.H * self.W * esz + (n_frames - 1) * gap
+        if buf.dtype != tt.uint8 or buf.device != self.device or buf.numel() < need:
+            raise ValueError('buf must be a uint8 tensor on %s with at least %d bytes' % (self.device, need))
+        if offset % esz or gap % esz:
+            raise ValueError('offset and gap must be multiples of the sample size')
+        lens = bool(kw.get('use_lens', True) and self.has_lens)
+        x0, y0, ow, oh = self._window(kw.get('window') if lens else None)
+        out = kw.get('out')
+        if out is None:
+            out = tt.empty((n_frames, oh, ow), dtype=kw.get('out_dtype') or tt.float32, device=self.device)
+        with self.ingest(big_endian, gap):
+            _lib.check(self.lib.imgcorr_correct_batch(
+                self._h, ctypes.c_void_p(buf.data_ptr() + offset), _dtype_code(dtype), ctypes.c_void_p(out.data_ptr()),
+                _dtype_code(out.dtype), n_frames, float(kw.get('threshold', 0.1)), int(kw.get('ksize', 3)),
+                int(kw.get('flags', DO_DARK | DO_FLAT | DO_NAN_TO_NUM)), int(lens), float(kw.get('border_value', 0.0)),
+                x0, y0, ow, oh, self._stream()))
+        return out
+
     # -- kernels ----------------------------------------------------------------------------
     def pointwise_median(self, raw, threshold=0.1, ksize=3, cond='>', flags=DO_DARK | DO_FLAT | DO_NAN_TO_NUM,
                          out_dtype=None, want_mask=False, out=None):
@@ -243,6 +290,11 @@ class Engine(object):
         D2H of consecutive frames overlap inside the library.  Synchronous."""
         squeeze = raw.ndim == 2
         raw = np.ascontiguousarray(raw)
+        big_endian = raw.dtype.byteorder == '>' or (raw.dtype.byteorder == '=' and not np.little_endian)
+        if big_endian:
+            if raw.dtype.itemsize != 2 or raw.dtype.kind != 'u':
+                raise TypeError('big-endian ingest is implemented for uint16 frames (got %s)' % raw.dtype)
+            raw = raw.view(raw.dtype.newbyteorder('<'))          # same bytes; K1 swaps them in its load
         if squeeze:
             raw = raw[None]
         if raw.shape[1:] != (self.H, self.W):
@@ -254,10 +306,11 @@ class Engine(object):
             out = np.empty((n, oh, ow), dtype=out_dtype)
         if not out.flags.c_contiguous or out.shape != (n, oh, ow):
             raise ValueError('out must be C-contiguous of shape %s' % ((n, oh, ow),))
-        _lib.check(self.lib.imgcorr_correct_host(
-            self._h, raw.ctypes.data_as(ctypes.c_void_p), NP_CODES[raw.dtype], out.ctypes.data_as(ctypes.c_void_p),
-            NP_CODES[out.dtype], n, float(threshold), int(ksize), int(flags), int(lens), float(border_value),
-            x0, y0, ow, oh))
+        with self.ingest(big_endian, 0):
+            _lib.check(self.lib.imgcorr_correct_host(
+                self._h, raw.ctypes.data_as(ctypes.c_void_p), NP_CODES[raw.dtype], out.ctypes.data_as(ctypes.c_void_p),
+                NP_CODES[out.dtype], n, float(threshold), int(ksize), int(flags), int(lens), float(border_value),
+                x0, y0, ow, oh))
         return out[0] if squeeze else out
 
 

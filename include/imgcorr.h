@@ -68,7 +68,11 @@ enum {
     IMGCORR_OPT_K1_SEG_ROWS = 4, /* rows per work unit of the streaming K1 kernel (0 = default) */
     IMGCORR_OPT_PROFILE = 5,     /* n > 0: bracket the K1 and K2 launch of every n-th frame group of the chain with CUDA
                                     events on the launching stream (read with imgcorr_profile_read); 0 = off */
-    IMGCORR_OPT_CHAIN_GROUP = 6  /* frames per K1 / K2 launch inside imgcorr_correct_batch (default 16) */
+    IMGCORR_OPT_CHAIN_GROUP = 6, /* frames per K1 / K2 launch inside imgcorr_correct_batch (default 16) */
+    /* ingest formats, consumed as stored in the file; they apply to every raw_dev of the context until reset: */
+    IMGCORR_OPT_RAW_BIG_ENDIAN = 7, /* uint16 samples are big-endian: reader/RAW.py:19-20 (littleEndian=False is its default) */
+    IMGCORR_OPT_RAW_FRAME_GAP = 8   /* bytes between the end of one raw frame and the start of the next: reader/elbin.py:23-32
+                                       (a 20-byte header precedes every frame).  Not available for the *_host entry point. */
 };
 
 IMGCORR_API const char* imgcorr_last_error(void);

@@ -160,6 +160,29 @@ def main():
         save('maps_' + tag, K=l.coeffs['cameraMatrix'], dist=l.coeffs['distortionCoeffs'], P=P,
              roi=np.array(roi), mapx=mx, mapy=my, shape=np.array([hh, ww]))
 
+    # ---- 10: ingest formats: the reference's own readers on two tiny files -------------
+    from imgProcessor.reader.RAW import RAW
+    from imgProcessor.reader.elbin import elbin
+    rng = np.random.default_rng(77)
+    rw, rh = 24, 32                                            # RAW(filename, width, height): array shape (width, height)
+    be = rng.integers(0, 65536, (rw, rh)).astype('>u2')
+    be.tofile(os.path.join(HERE, 'raw_be_u16_24x32.raw'))
+    got = RAW(os.path.join(HERE, 'raw_be_u16_24x32.raw'), rw, rh, '16-bit Unsigned')
+    assert got.dtype == np.dtype('>u2') and got.shape == (rw, rh)
+    eh, ew, en = 40, 24, 3                                     # elbin header: height, width, frames; frames shaped (width, height)
+    with open(os.path.join(HERE, 'stack_3x24x40.elbin'), 'wb') as f:
+        f.write(np.array([eh, ew, en], np.uint32).tobytes())
+        frames = rng.integers(0, 65536, (en, ew, eh)).astype(np.uint16)
+        for i in range(en):
+            f.write(np.array([1.5 + i, 30.25 - i], np.float64).tobytes())
+            f.write(np.array([3 + i], np.uint32).tobytes())
+            f.write(frames[i].tobytes())
+    arrs, labels = elbin(os.path.join(HERE, 'stack_3x24x40.elbin'))
+    assert np.array_equal(arrs, frames)
+    save('readers', raw_be=np.asarray(got, dtype=np.uint16), elbin_frames=arrs,
+         elbin_times=np.array([l['exposure time[s]'] for l in labels]),
+         elbin_current=np.array([l['current[A]'] for l in labels]), elbin_voltage=np.array([l['voltage[V]'] for l in labels]))
+
     with open(os.path.join(HERE, 'versions.json'), 'w') as f:
         json.dump({'numpy': np.__version__, 'scipy': scipy.__version__, 'cv2': cv2.__version__,
                    'reference': 'radjkarl/imgProcessor 0.2.5 (/root/reference), unmodified, under ref_shim'}, f, indent=1)
