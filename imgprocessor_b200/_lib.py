@@ -12,6 +12,7 @@ COND_GT, COND_LT = 0, 1
 DO_DARK, DO_FLAT, DO_NAN_TO_NUM = 1, 2, 4
 OPT_K1_VARIANT, OPT_K2_VARIANT, OPT_HOST_SLOTS, OPT_K1_SEG_ROWS, OPT_PROFILE, OPT_CHAIN_GROUP = 1, 2, 3, 4, 5, 6
 OPT_RAW_BIG_ENDIAN, OPT_RAW_FRAME_GAP = 7, 8
+INTER_CUBIC, INTER_LANCZOS4 = 2, 4
 OK, ERR_INVALID, ERR_CUDA, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
 
 c_void_p, c_int, c_double, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
@@ -40,6 +41,9 @@ SIGNATURES = {
                                       c_double, c_int, c_int, c_int, c_int, c_void_p]),
     'imgcorr_correct_host': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_double, c_int, c_int, c_int,
                                      c_double, c_int, c_int, c_int, c_int]),
+    'imgcorr_warp_perspective': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
+                                         c_int, c_int, c_double, c_void_p]),
+    'imgcorr_divide_f64': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'imgcorr_host_alloc': (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),
     'imgcorr_host_free': (c_int, [c_void_p]),
 }

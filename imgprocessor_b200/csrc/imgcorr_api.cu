@@ -63,6 +63,7 @@ struct imgcorr_ctx {
     double dark_absmax = 0.0, flat_absmin = 1.0;   // over finite entries (flat: non-zero entries)
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
+    float* warp_tab = nullptr;                // [32][8] Lanczos4 then [32][4] bicubic coefficient tables (K3)
     // host pipeline
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
     std::vector<HostSlot> slots;
@@ -146,6 +147,7 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->mid[0]);
     cudaFree(c->mid[1]);
     cudaFree(c->lens_dev);
+    cudaFree(c->warp_tab);
     cudaFree(c->dump);
     for (int k = 0; k < 2; ++k) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     delete c;
@@ -424,6 +426,58 @@ extern "C" IMGCORR_API int imgcorr_undistort_maps(imgcorr_ctx* c, float* mapx_de
     cudaError_t e = launch_write_maps(c->lens, mapx_dev, mapy_dev, c->H, c->W, (cudaStream_t)stream, &l);
     c->launches += l;
     if (e != cudaSuccess) return cuda_fail(e, "map kernel launch");
+    return IMGCORR_OK;
+}
+
+// ---- K3 -------------------------------------------------------------------------------------
+extern "C" IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* c, const void* src_dev, int dtype, int src_h, int src_w,
+                                        void* dst_dev, int dst_h, int dst_w, int n_frames, const double M[9],
+                                        int interpolation, int inverse_map, double border_value, void* stream) {
+    GUARD(c);
+    if (!src_dev || !dst_dev || !M) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (dtype == DT_U8) return fail(IMGCORR_ERR_INVALID, "warp_perspective: uint8 images are not implemented (OpenCV's int16 fixed-point weights)");
+    if (dtype != DT_U16 && dtype != DT_F32 && dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
+    if (interpolation != IMGCORR_INTER_LANCZOS4 && interpolation != IMGCORR_INTER_CUBIC)
+        return fail(IMGCORR_ERR_INVALID, "interpolation must be IMGCORR_INTER_LANCZOS4 or IMGCORR_INTER_CUBIC");
+    if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || src_h > 32767 || src_w > 32767 || dst_h > 32767 || dst_w > 32767)
+        return fail(IMGCORR_ERR_INVALID, "bad frame shape (%d x %d -> %d x %d)", src_h, src_w, dst_h, dst_w);
+    if (n_frames < 0) return fail(IMGCORR_ERR_INVALID, "n_frames < 0");
+    if (!c->warp_tab) {
+        float h[32 * 8 + 32 * 4];
+        warp_lanczos4_table(h);
+        warp_cubic_table(h + 32 * 8);
+        CK(cudaMalloc(&c->warp_tab, sizeof(h)));
+        CK(cudaMemcpy(c->warp_tab, h, sizeof(h), cudaMemcpyHostToDevice));
+    }
+    K3Args a;
+    a.src = src_dev;
+    a.dst = dst_dev;
+    a.H = src_h;
+    a.W = src_w;
+    a.dh = dst_h;
+    a.dw = dst_w;
+    a.n_frames = n_frames;
+    a.border = border_for_dtype(0, dtype == DT_U16, border_value);
+    a.wc = make_warp_const(M, inverse_map, dst_w, dst_h);
+    a.tab = interpolation == IMGCORR_INTER_LANCZOS4 ? c->warp_tab : c->warp_tab + 32 * 8;
+    int l = 0;
+    cudaError_t e = launch_k3(a, dtype, interpolation, (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "K3 launch");
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* c, const void* src_dev, int src_dtype, const double* divisor_dev,
+                                  double* dst_dev, size_t pixels_per_frame, int n_frames, void* stream) {
+    GUARD(c);
+    if (!src_dev || !divisor_dev || !dst_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (src_dtype < DT_U8 || src_dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", src_dtype);
+    if (n_frames < 0) return fail(IMGCORR_ERR_INVALID, "n_frames < 0");
+    int l = 0;
+    cudaError_t e = launch_k3_divide(src_dev, src_dtype, divisor_dev, dst_dev, pixels_per_frame, n_frames, c->sm_count,
+                                     (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "divide kernel launch");
     return IMGCORR_OK;
 }
 

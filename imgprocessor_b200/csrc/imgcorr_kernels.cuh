@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "imgcorr_core.cuh"
+#include "imgcorr_warp.cuh"
 
 namespace imgcorr {
 
@@ -61,5 +62,18 @@ cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant
                       int* launches);
 cudaError_t launch_write_maps(const LensConst& lens, float* mapx, float* mapy, int H, int W,
                               cudaStream_t stream, int* launches);
+
+// K3: perspective warp (cv2.warpPerspective, Lanczos4 / bicubic) ------------------------------
+struct K3Args {
+    const void* src;        // [n_frames][H][W]
+    void* dst;              // [n_frames][dh][dw], same dtype
+    int H, W, dh, dw, n_frames;
+    double border;          // already converted to the image dtype's value range
+    WarpConst wc;
+    const float* tab;       // device coefficient table [32][N] of the interpolation
+};
+cudaError_t launch_k3(const K3Args& a, int dtype, int interp, cudaStream_t stream, int* launches);
+cudaError_t launch_k3_divide(const void* src, int dtype, const double* div, double* dst, size_t npx, int n_frames,
+                             int sm_count, cudaStream_t stream, int* launches);
 
 }  // namespace imgcorr

@@ -259,6 +259,34 @@ class Engine(object):
             float(border_value), self._stream()))
         return out[0] if squeeze else out
 
+    def warp_perspective(self, src, M, dsize, interpolation='lanczos4', inverse_map=False, border_value=0.0,
+                         divide_by=None):
+        """K3: cv2.warpPerspective(src, M, dsize=(width, height), flags=INTER_LANCZOS4 | INTER_CUBIC
+        [| WARP_INVERSE_MAP], borderValue) for device frames [n,h,w] or [h,w] of uint16 / float32 / float64
+        (camera/PerspectiveCorrection.py:374-378, 401-405).  divide_by: float64 [h,w] tilt factor applied first
+        in float64 (:394-400); the result is then float64.  The frame shape is free (not the engine's)."""
+        tt = torch()
+        squeeze = src.dim() == 2
+        src = (src[None] if squeeze else src).to(self.device).contiguous()
+        n, h, w = src.shape
+        dw, dh = int(dsize[0]), int(dsize[1])
+        if divide_by is not None:
+            div = divide_by.to(device=self.device, dtype=tt.float64).contiguous()
+            if tuple(div.shape) != (h, w):
+                raise ValueError('divide_by must be [h,w]')
+            q = tt.empty((n, h, w), dtype=tt.float64, device=self.device)
+            _lib.check(self.lib.imgcorr_divide_f64(self._h, ctypes.c_void_p(src.data_ptr()), _dtype_code(src.dtype),
+                                                   ctypes.c_void_p(div.data_ptr()), ctypes.c_void_p(q.data_ptr()),
+                                                   h * w, n, self._stream()))
+            src = q
+        Mh = np.ascontiguousarray(np.asarray(M, np.float64).reshape(3, 3))
+        out = tt.empty((n, dh, dw), dtype=src.dtype, device=self.device)
+        _lib.check(self.lib.imgcorr_warp_perspective(
+            self._h, ctypes.c_void_p(src.data_ptr()), _dtype_code(src.dtype), h, w, ctypes.c_void_p(out.data_ptr()),
+            dh, dw, n, Mh.ctypes.data_as(ctypes.c_void_p), {'lanczos4': _lib.INTER_LANCZOS4, 'cubic': _lib.INTER_CUBIC}[interpolation],
+            int(bool(inverse_map)), float(border_value), self._stream()))
+        return out[0] if squeeze else out
+
     def undistort_maps(self):
         tt = torch()
         mapx = tt.empty((self.H, self.W), dtype=tt.float32, device=self.device)

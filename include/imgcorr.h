@@ -154,6 +154,25 @@ IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* ctx, const void* raw_host, int
                          int n_frames, double threshold, int ksize, int flags, int use_lens, double border_value,
                          int x0, int y0, int ow, int oh);
 
+/* ---- K3: perspective warp -----------------------------------------------------
+ * Replaces cv2.warpPerspective in PerspectiveCorrection.correct (flags=INTER_LANCZOS4,
+ * camera/PerspectiveCorrection.py:401-405) and PerspectiveCorrection.uncorrect (INTER_CUBIC |
+ * WARP_INVERSE_MAP, :374-378), bit-exact with OpenCV's arithmetic (BORDER_CONSTANT).
+ *   src_dev [n][src_h][src_w], dst_dev [n][dst_h][dst_w], both of `dtype` (U16, F32 or F64; uint8's int16
+ *   fixed-point weights are not implemented -> IMGCORR_ERR_INVALID); frame sizes are free (<= 32767 per side),
+ *   the context only supplies the device.
+ *   M             3x3 row-major homography src -> dst (the matrix cv2.warpPerspective takes); inverted here
+ *                 with cv::invert's cofactor formula unless inverse_map != 0
+ *   interpolation IMGCORR_INTER_LANCZOS4 or IMGCORR_INTER_CUBIC (values of the cv2 flags) */
+enum { IMGCORR_INTER_CUBIC = 2, IMGCORR_INTER_LANCZOS4 = 4 };
+IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* ctx, const void* src_dev, int dtype, int src_h, int src_w, void* dst_dev,
+                             int dst_h, int dst_w, int n_frames, const double M[9], int interpolation, int inverse_map,
+                             double border_value, void* stream);
+/* dst[f][i] = (double)src[f][i] / divisor[i]: the tilt-factor division in front of the warp
+ * (camera/PerspectiveCorrection.py:394-400, np.asfarray(img) / tf).  src of any dtype, divisor and dst float64. */
+IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* ctx, const void* src_dev, int src_dtype, const double* divisor_dev, double* dst_dev,
+                       size_t pixels_per_frame, int n_frames, void* stream);
+
 /* page-locked host memory for the *_host entry points */
 IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr);
 IMGCORR_API int imgcorr_host_free(void* ptr);

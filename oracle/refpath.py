@@ -112,3 +112,25 @@ def correct(image, dark=None, flat=None, lens=None, threshold=0.1, keep_size=Tru
     if lens is not None:
         image = lens_correct(image, lens[0], lens[1], keep_size=keep_size)
     return image
+
+
+# ---- SURVEY §8 row f3 -------------------------------------------------------------------
+def perspective_correct(image, homography, new_size, tilt_factor=None, **cv2_opts):
+    """PerspectiveCorrection.correct (camera/PerspectiveCorrection.py:380-406) for a fixed homography:
+    optional ``np.asfarray(img) / tiltFactor`` (:394-400), then
+    ``cv2.warpPerspective(img, h, newBorders[::-1], flags=cv2.INTER_LANCZOS4, **cv2_opts)`` (:401-405).
+    new_size = (sizey, sizex) as in the reference's constructor."""
+    import cv2
+    img = np.asarray(image)
+    if tilt_factor is not None:
+        img = np.asarray(img, dtype=np.float64) / tilt_factor
+    return cv2.warpPerspective(img, np.asarray(homography, np.float64), tuple(new_size)[::-1], flags=cv2.INTER_LANCZOS4,
+                               **cv2_opts)
+
+
+def perspective_uncorrect(image, homography):
+    """PerspectiveCorrection.uncorrect (camera/PerspectiveCorrection.py:374-378)."""
+    import cv2
+    img = np.asarray(image)
+    return cv2.warpPerspective(img, np.asarray(homography, np.float64), img.shape[:2][::-1],
+                               flags=cv2.INTER_CUBIC | cv2.WARP_INVERSE_MAP)

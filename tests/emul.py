@@ -9,6 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'host_emul', 'emul.cpp')
 CORE = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_core.cuh')
+WARP = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_warp.cuh')
 NET = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'median25_net.inc')
 OUT = os.path.join(HERE, '_build', 'libimgcorr_emul.so')
 _DT = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}
@@ -19,7 +20,7 @@ def lib():
     global _lib
     if _lib is None:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NET)):
+        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NET), os.path.getmtime(WARP)):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
                                    '-fvisibility=hidden', '-o', OUT, SRC, '-lm'])
         _lib = ctypes.CDLL(OUT)
@@ -69,4 +70,25 @@ def remap(src, mapx, mapy, border=0.0, window=None, widen=False):
     dst = np.empty((oh, ow), out_dtype)
     lib().emul_remap(_p(src), dt, _p(dst), H, W, _p(np.ascontiguousarray(mapx, np.float32)),
                      _p(np.ascontiguousarray(mapy, np.float32)), ctypes.c_double(border), x0, y0, ow, oh)
+    return dst
+
+
+def warp_tables(M=None):
+    """(lanczos4 [32][8], cubic [32][4], inverse of M by the cv::invert formula)"""
+    lz = np.empty((32, 8), np.float32)
+    cu = np.empty((32, 4), np.float32)
+    M = np.ascontiguousarray(np.eye(3) if M is None else M, np.float64)
+    Mi = np.empty((3, 3), np.float64)
+    lib().emul_warp_tables(_p(lz), _p(cu), _p(M), _p(Mi))
+    return lz, cu, Mi
+
+
+def warp(src, M, dsize, interpolation='lanczos4', inverse_map=False, border=0.0):
+    src = np.ascontiguousarray(src)
+    H, W = src.shape
+    dw, dh = int(dsize[0]), int(dsize[1])
+    dst = np.empty((dh, dw), src.dtype)
+    r = lib().emul_warp(_p(src), _DT[src.dtype], _p(dst), H, W, dh, dw, _p(np.ascontiguousarray(M, np.float64)),
+                        {'lanczos4': 4, 'cubic': 2}[interpolation], int(bool(inverse_map)), ctypes.c_double(border))
+    assert r == 0
     return dst

@@ -188,5 +188,38 @@ def main():
                    'reference': 'radjkarl/imgProcessor 0.2.5 (/root/reference), unmodified, under ref_shim'}, f, indent=1)
 
 
+def perspective():
+    """PerspectiveCorrection.correct / uncorrect of the unmodified reference
+    (camera/PerspectiveCorrection.py:374-406) with a homography and with a quad reference."""
+    ref_shim.install_perspective_stubs()
+    from imgProcessor.camera.PerspectiveCorrection import PerspectiveCorrection
+    H, W = 120, 160
+    scene = synth.scene(H, W, seed=21, dtype=np.float64, full_scale=1.0).astype(np.float64)
+    quad = np.array([[14.5, 9.0], [150.25, 17.0], [141.0, 110.5], [8.0, 101.0]])
+    new_size = (96, 136)                                       # (sizey, sizex)
+    out = {}
+    for tag, img in (('f64', scene), ('f32', scene.astype(np.float32)), ('u16', (scene * 65535).astype(np.uint16))):
+        pc = PerspectiveCorrection(img.shape, new_size=new_size, border=4)
+        pc.setReference(quad[[2, 0, 3, 1]])                    # unsorted on purpose: sortCorners orders it
+        out['quad_' + tag], log = quiet(pc.correct, img)
+        if tag == 'f64':
+            out['quad_sorted'] = pc.quad.copy()
+            out['quad_homography'] = np.array(pc.homography)
+            out['uncorrect_f64'] = pc.uncorrect(out['quad_f64'])
+    Hm = np.array([[1.02, 0.03, -6.5], [-0.015, 0.97, 4.25], [2e-5, -4e-5, 1.0]])
+    pc = PerspectiveCorrection(scene.shape, new_size=(H, W))
+    pc.setReference(Hm)
+    out['homography_f64'] = quiet(pc.correct, scene)[0]
+    out['homography_f32'] = quiet(pc.correct, scene.astype(np.float32))[0]
+    pc = PerspectiveCorrection(scene.shape, new_size=(H + 30, W + 50), cv2_opts={'borderValue': 0.25})
+    pc.setReference(Hm)
+    out['homography_border_f32'] = quiet(pc.correct, scene.astype(np.float32))[0]
+    save('perspective', scene=scene, quad=quad[[2, 0, 3, 1]], new_size=np.array(new_size), border=np.int64(4), Hm=Hm, log=np.array(log), **out)
+
+
 if __name__ == '__main__':
-    main()
+    if sys.argv[1:] == ['perspective']:
+        perspective()
+    else:
+        main()
+        perspective()

@@ -37,3 +37,19 @@ def install():
     mod('fancytools.math.linRegressUsingMasked2dArrays', linRegressUsingMasked2dArrays=None)
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
+
+
+def install_perspective_stubs():
+    """Extra import-time-only stand-ins for camera/PerspectiveCorrection.py:8-22 (transforms3d and more of
+    fancytools are absent).  None of them is reached by PerspectiveCorrection.correct / uncorrect with a
+    homography or quad reference and do_correctIntensity=False, which is what the golden files record."""
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+    mod('transforms3d')
+    mod('transforms3d.euler', mat2euler=None, euler2mat=None)
+    mod('fancytools.math.Point3D', Point3D=None)
+    mod('fancytools.math.vector3d', vectorAngle=None)
+    sys.modules['fancytools.math'].line = mod('fancytools.math.line')

@@ -139,3 +139,38 @@ void emul_remap(const void* src, int dtype, void* dst, int H, int W, const float
             }
         }
 }
+
+// ---- cv2.warpPerspective (imgcorr_warp.cuh) -------------------------------------------
+#include "../../imgprocessor_b200/csrc/imgcorr_warp.cuh"
+
+extern "C" __attribute__((visibility("default")))
+void emul_warp_tables(float* lanczos, float* cubic, const double* M, double* Minv) {
+    warp_lanczos4_table(lanczos);
+    warp_cubic_table(cubic);
+    warp_invert3x3(M, Minv);
+}
+
+template <typename T, typename AT, int N>
+static void warp_typed(const T* src, T* dst, int H, int W, int dh, int dw, const WarpConst& wc, const float* tab, double border) {
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) {
+            AT v = warp_pixel<T, AT, N>(src, H, W, warp_coord(wc, x, y), tab, (AT)border);
+            if (sizeof(T) == 2) dst[(size_t)y * dw + x] = (T)sat_u16((float)v);
+            else dst[(size_t)y * dw + x] = (T)v;
+        }
+}
+
+// dtype: 1 u16, 2 f32, 3 f64;  interp: 2 cubic, 4 lanczos4
+extern "C" __attribute__((visibility("default")))
+int emul_warp(const void* src, int dtype, void* dst, int H, int W, int dh, int dw, const double* M, int interp, int inverse,
+              double border) {
+    std::vector<float> tab(32 * 8);
+    if (interp == WARP_LANCZOS4) warp_lanczos4_table(tab.data()); else if (interp == WARP_CUBIC) warp_cubic_table(tab.data()); else return -1;
+    WarpConst wc = make_warp_const(M, inverse, dw, dh);
+    border = border_for_dtype(0, dtype == 1, border);
+#define GO(T, AT) { if (interp == WARP_LANCZOS4) warp_typed<T, AT, 8>((const T*)src, (T*)dst, H, W, dh, dw, wc, tab.data(), border); \
+                    else warp_typed<T, AT, 4>((const T*)src, (T*)dst, H, W, dh, dw, wc, tab.data(), border); }
+    if (dtype == 1) GO(uint16_t, float) else if (dtype == 2) GO(float, float) else if (dtype == 3) GO(double, double) else return -1;
+#undef GO
+    return 0;
+}

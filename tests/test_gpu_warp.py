@@ -1,0 +1,159 @@
+"""SURVEY §8 row f3 on the GPU: kernel K3 (csrc/k3_warp.cu) through the C ABI against OpenCV-exact arithmetic
+(oracle/warp.py, oracle/refpath.py) and the golden outputs of the reference's PerspectiveCorrection.
+Bar: bit-exact for uint16 / float32 / float64, Lanczos4 and bicubic, any border value."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import refpath
+from oracle import warp as W
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip('torch')
+cv2 = pytest.importorskip('cv2')
+
+
+@pytest.fixture(scope='module')
+def eng():
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from imgprocessor_b200 import engine
+    return engine.get_engine(8, 8)          # K3 takes free frame shapes; the context supplies the device
+
+
+MATS = [np.array([[0.5, 0.1, -20], [0.05, 0.7, -30], [1e-4, -2e-4, 1.0]]),
+        np.eye(3) + np.array([[0, 0, 5.3], [0, 0, -7.77], [0, 0, 0]]),
+        np.array([[1.3, -0.2, 12.5], [0.1, 1.1, -3.0], [-3e-4, 1e-4, 1.0]])]
+
+
+def _img(dt, shape, seed=0):
+    a = np.random.default_rng(seed).random(shape)
+    return (a * 65535).astype(np.uint16) if dt == np.uint16 else a.astype(dt)
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.float64, np.uint16])
+@pytest.mark.parametrize('interp', ['lanczos4', 'cubic'])
+def test_k3_bit_exact(eng, dt, interp):
+    img = _img(dt, (90, 130))
+    flag = cv2.INTER_LANCZOS4 if interp == 'lanczos4' else cv2.INTER_CUBIC
+    for M in MATS:
+        for dsize in ((130, 90), (37, 150), (200, 11), (1, 1)):
+            for inv in (False, True):
+                for border in (0.0, 1234.5):
+                    ref = cv2.warpPerspective(img, M, dsize, flags=flag | (cv2.WARP_INVERSE_MAP if inv else 0),
+                                              borderValue=border)
+                    got = eng.warp_perspective(_dev(img), M, dsize, interp, inv, border).cpu().numpy()
+                    assert np.array_equal(got, ref.reshape(got.shape)), (dt, interp, dsize, inv, border)
+                    assert np.array_equal(got, W.warp_perspective_model(img, M, dsize, interp, inv, border))
+
+
+def test_k3_tiny_sources(eng):
+    # sources smaller than the tap window: every pixel takes the border arithmetic
+    for shape in ((1, 1), (3, 5), (7, 7), (8, 8), (2, 40)):
+        img = _img(np.float32, shape, 2)
+        M = np.array([[1.1, 0.05, 0.4], [-0.02, 0.9, 0.3], [0, 0, 1.0]])
+        for interp, flag in (('lanczos4', cv2.INTER_LANCZOS4), ('cubic', cv2.INTER_CUBIC)):
+            ref = cv2.warpPerspective(img, M, (23, 17), flags=flag, borderValue=0.5)
+            got = eng.warp_perspective(_dev(img), M, (23, 17), interp, False, 0.5).cpu().numpy()
+            assert np.array_equal(got, ref)
+
+
+def test_k3_degenerate_and_special_values(eng):
+    img = _img(np.float32, (40, 50))
+    for M in (np.zeros((3, 3)), np.array([[1, 0, 0], [0, 1, 0], [0.05, 0, -1.0]]),
+              np.array([[1e6, 0, 0], [0, 1e6, 0], [0, 0, 1.0]]), np.array([[1e-7, 0, 3], [0, 1e-7, 4], [0, 0, 1.0]])):
+        for inv in (False, True):
+            ref = cv2.warpPerspective(img, M, (64, 48), flags=cv2.INTER_LANCZOS4 | (cv2.WARP_INVERSE_MAP if inv else 0))
+            got = eng.warp_perspective(_dev(img), M, (64, 48), 'lanczos4', inv).cpu().numpy()
+            assert np.array_equal(got, ref, equal_nan=True)
+    img[10, 10] = np.inf
+    img[20, 30] = np.nan
+    img[5, 40] = -np.inf
+    ref = cv2.warpPerspective(img, MATS[2], (60, 50), flags=cv2.INTER_LANCZOS4)
+    got = eng.warp_perspective(_dev(img), MATS[2], (60, 50)).cpu().numpy()
+    assert np.array_equal(got, ref, equal_nan=True)
+
+
+def test_k3_batch_and_division(eng):
+    frames = np.stack([_img(np.uint16, (120, 160), s) for s in range(5)])
+    M = MATS[0]
+    got = eng.warp_perspective(_dev(frames), M, (140, 100)).cpu().numpy()
+    for i in range(5):
+        assert np.array_equal(got[i], cv2.warpPerspective(frames[i], M, (140, 100), flags=cv2.INTER_LANCZOS4))
+    tf = 0.5 + np.random.default_rng(5).random((120, 160))
+    got = eng.warp_perspective(_dev(frames), M, (140, 100), divide_by=torch.from_numpy(tf)).cpu().numpy()
+    assert got.dtype == np.float64
+    for i in range(5):
+        assert np.array_equal(got[i], refpath.perspective_correct(frames[i], M, (100, 140), tilt_factor=tf))
+
+
+def test_k3_full_frame(eng):
+    # BASELINE frame size, a mild keystone: against OpenCV itself (the model needs minutes at 12 Mpx)
+    H, Wd = 3000, 4096
+    img = _img(np.float32, (H, Wd), 7)
+    quad = np.float32([[60, 40], [4040, 75], [4000, 2950], [30, 2900]])
+    dst = np.float32([[0, 0], [Wd, 0], [Wd, H], [0, H]])
+    M = cv2.getPerspectiveTransform(quad, dst)
+    ref = cv2.warpPerspective(img, M, (Wd, H), flags=cv2.INTER_LANCZOS4)
+    got = eng.warp_perspective(_dev(img), M, (Wd, H)).cpu().numpy()
+    assert np.array_equal(got, ref)
+    u16 = (img * 65535).astype(np.uint16)
+    assert np.array_equal(eng.warp_perspective(_dev(u16), M, (Wd, H)).cpu().numpy(),
+                          cv2.warpPerspective(u16, M, (Wd, H), flags=cv2.INTER_LANCZOS4))
+
+
+def test_k3_rejects(eng):
+    from imgprocessor_b200._lib import ImgcorrError
+    with pytest.raises(ImgcorrError):
+        eng.warp_perspective(_dev(np.zeros((8, 8), np.uint8)), np.eye(3), (8, 8))
+
+
+def test_perspective_correction_api_golden():
+    """the Python mirror against the unmodified reference's outputs"""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from imgprocessor_b200.camera import PerspectiveCorrection
+    g = load_golden('perspective')
+    scene = g['scene']
+    ns = tuple(int(v) for v in g['new_size'])
+    for tag, img in (('f64', scene), ('f32', scene.astype(np.float32)), ('u16', (scene * 65535).astype(np.uint16))):
+        pc = PerspectiveCorrection(img.shape, new_size=ns, border=int(g['border']))
+        pc.setReference(g['quad'])
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            out = pc.correct(img)
+        assert buf.getvalue() == str(g['log'])
+        assert out.dtype == img.dtype and np.array_equal(out, g['quad_' + tag])
+        if tag == 'f64':
+            assert np.array_equal(pc.quad, g['quad_sorted'])
+            assert np.array_equal(pc.homography, g['quad_homography'])
+            assert np.array_equal(pc.uncorrect(out), g['uncorrect_f64'])
+    pc = PerspectiveCorrection(scene.shape, new_size=scene.shape)
+    pc.setReference(g['Hm'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        assert np.array_equal(pc.correct(scene), g['homography_f64'])
+        assert np.array_equal(pc.correct(scene.astype(np.float32)), g['homography_f32'])
+        t = pc.correct(torch.from_numpy(scene.astype(np.float32)).cuda())          # device tensors stay on the device
+        assert t.is_cuda and np.array_equal(t.cpu().numpy(), g['homography_f32'])
+    pc = PerspectiveCorrection(scene.shape, new_size=(scene.shape[0] + 30, scene.shape[1] + 50), cv2_opts={'borderValue': 0.25})
+    pc.setReference(g['Hm'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        assert np.array_equal(pc.correct(scene.astype(np.float32)), g['homography_border_f32'])
+    # tilt-factor division + warp
+    tf = 0.5 + np.random.default_rng(5).random(scene.shape)
+    pc = PerspectiveCorrection(scene.shape, new_size=ns, do_correctIntensity=True)
+    pc.setReference(g['Hm'])
+    with pytest.raises(NotImplementedError):
+        pc.correct(scene)
+    pc.setTiltFactor(tf)
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = pc.correct((scene * 65535).astype(np.uint16))
+    assert np.array_equal(out, refpath.perspective_correct((scene * 65535).astype(np.uint16), g['Hm'], ns, tilt_factor=tf))
