@@ -53,7 +53,7 @@ struct imgcorr_ctx {
     void* dump = nullptr;                     // scratch for stores of lanes that own no output pixel
     int raw_big_endian = 0;
     long long raw_gap = 0;
-    int k1_variant = 0, k2_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 16;
+    int k1_variant = 0, k2_variant = 0, k3_variant = 0, host_slots = 4, k1_seg_rows = 0, profile = 0, chain_group = 16;
     long long chain_groups_seen = 0;
     double prof_frames[2] = {0.0, 0.0};
     std::vector<cudaEvent_t> prof_ev[2];      // [kernel] start/stop pairs
@@ -163,6 +163,10 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
             c->k2_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_K3_VARIANT:
+            if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k3 variant %d", value);
+            c->k3_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_PROFILE:
             if (value < 0) return fail(IMGCORR_ERR_INVALID, "profile stride %d", value);
@@ -461,8 +465,9 @@ extern "C" IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* c, const void* 
     a.wc = make_warp_const(M, inverse_map, dst_w, dst_h);
     a.tab = interpolation == IMGCORR_INTER_LANCZOS4 ? c->warp_tab : c->warp_tab + 32 * 8;
     int l = 0;
-    cudaError_t e = launch_k3(a, dtype, interpolation, (cudaStream_t)stream, &l);
+    cudaError_t e = launch_k3(a, dtype, interpolation, c->k3_variant, (cudaStream_t)stream, &l);
     c->launches += l;
+    if (e == cudaErrorNotSupported) return fail(IMGCORR_ERR_INVALID, "the requested K3 variant is not eligible for this call");
     if (e != cudaSuccess) return cuda_fail(e, "K3 launch");
     return IMGCORR_OK;
 }

@@ -72,7 +72,7 @@ struct K3Args {
     WarpConst wc;
     const float* tab;       // device coefficient table [32][N] of the interpolation
 };
-cudaError_t launch_k3(const K3Args& a, int dtype, int interp, cudaStream_t stream, int* launches);
+cudaError_t launch_k3(const K3Args& a, int dtype, int interp, int variant, cudaStream_t stream, int* launches);
 cudaError_t launch_k3_divide(const void* src, int dtype, const double* div, double* dst, size_t npx, int n_frames,
                              int sm_count, cudaStream_t stream, int* launches);
 

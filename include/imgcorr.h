@@ -71,8 +71,9 @@ enum {
     IMGCORR_OPT_CHAIN_GROUP = 6, /* frames per K1 / K2 launch inside imgcorr_correct_batch (default 16) */
     /* ingest formats, consumed as stored in the file; they apply to every raw_dev of the context until reset: */
     IMGCORR_OPT_RAW_BIG_ENDIAN = 7, /* uint16 samples are big-endian: reader/RAW.py:19-20 (littleEndian=False is its default) */
-    IMGCORR_OPT_RAW_FRAME_GAP = 8   /* bytes between the end of one raw frame and the start of the next: reader/elbin.py:23-32
+    IMGCORR_OPT_RAW_FRAME_GAP = 8,  /* bytes between the end of one raw frame and the start of the next: reader/elbin.py:23-32
                                        (a 20-byte header precedes every frame).  Not available for the *_host entry point. */
+    IMGCORR_OPT_K3_VARIANT = 9      /* 0 auto, 1 gathers through L1/L2, 2 shared-memory staged tiles (uint16 / float32 sources; fails if not eligible) */
 };
 
 IMGCORR_API const char* imgcorr_last_error(void);

@@ -17,17 +17,45 @@ torch = pytest.importorskip('torch')
 cv2 = pytest.importorskip('cv2')
 
 
-@pytest.fixture(scope='module')
-def eng():
+@pytest.fixture(scope='module', params=[0, 1, 2], ids=['auto', 'l1', 'tiles'])
+def eng(request):
     if not torch.cuda.is_available():
         pytest.skip('needs a CUDA device')
-    from imgprocessor_b200 import engine
-    return engine.get_engine(8, 8)          # K3 takes free frame shapes; the context supplies the device
+    from imgprocessor_b200 import engine, _lib
+    e = engine.get_engine(8, 8)             # K3 takes free frame shapes; the context supplies the device
+    # 2 = shared-memory tiles forced: the fixture falls back per call where a shape is not eligible
+    e.set_option(_lib.OPT_K3_VARIANT, request.param)
+    yield _Eng(e, request.param)
+    e.set_option(_lib.OPT_K3_VARIANT, 0)
 
 
 MATS = [np.array([[0.5, 0.1, -20], [0.05, 0.7, -30], [1e-4, -2e-4, 1.0]]),
         np.eye(3) + np.array([[0, 0, 5.3], [0, 0, -7.77], [0, 0, 0]]),
         np.array([[1.3, -0.2, 12.5], [0.1, 1.1, -3.0], [-3e-4, 1e-4, 1.0]])]
+
+
+class _Eng(object):
+    """engine wrapper: with the tiles forced (param 2) a call that is not eligible for them (float64, rows that are
+    not 16-byte multiples) is repeated on the automatic path"""
+
+    def __init__(self, e, param):
+        self.e, self.param = e, param
+
+    def set_option(self, k, v):
+        self.e.set_option(k, v)
+
+    def warp_perspective(self, *a, **k):
+        from imgprocessor_b200 import _lib
+        try:
+            return self.e.warp_perspective(*a, **k)
+        except _lib.ImgcorrError as err:
+            if self.param != 2 or 'not eligible' not in str(err):
+                raise
+            self.e.set_option(_lib.OPT_K3_VARIANT, 0)
+            try:
+                return self.e.warp_perspective(*a, **k)
+            finally:
+                self.e.set_option(_lib.OPT_K3_VARIANT, 2)
 
 
 def _img(dt, shape, seed=0):
@@ -111,9 +139,42 @@ def test_k3_full_frame(eng):
 
 
 def test_k3_rejects(eng):
-    from imgprocessor_b200._lib import ImgcorrError
-    with pytest.raises(ImgcorrError):
+    from imgprocessor_b200 import _lib
+    with pytest.raises(_lib.ImgcorrError):
         eng.warp_perspective(_dev(np.zeros((8, 8), np.uint8)), np.eye(3), (8, 8))
+    param, eng = eng.param, eng.e
+    eng.set_option(_lib.OPT_K3_VARIANT, 2)
+    try:
+        with pytest.raises(_lib.ImgcorrError):      # rows of 130 float32 are not 16-byte multiples: tiles not eligible
+            eng.warp_perspective(_dev(np.zeros((8, 130), np.float32)), np.eye(3), (8, 8))
+        with pytest.raises(_lib.ImgcorrError):
+            eng.warp_perspective(_dev(np.zeros((8, 128), np.float64)), np.eye(3), (8, 8))
+        out = eng.warp_perspective(_dev(_img(np.float32, (64, 128))), MATS[1], (128, 64)).cpu().numpy()
+        assert np.array_equal(out, cv2.warpPerspective(_img(np.float32, (64, 128)), MATS[1], (128, 64), flags=cv2.INTER_LANCZOS4))
+    finally:
+        eng.set_option(_lib.OPT_K3_VARIANT, param)
+
+
+@pytest.mark.parametrize('dt', [np.float32, np.uint16])
+@pytest.mark.parametrize('interp', ['lanczos4', 'cubic'])
+def test_k3_tiled_shapes(eng, dt, interp):
+    # widths that are 16-byte multiples (tile path), homographies from identity to strong zoom-out / rotation
+    # (tiles whose window does not fit the staged box fall back to global gathers)
+    flag = cv2.INTER_LANCZOS4 if interp == 'lanczos4' else cv2.INTER_CUBIC
+    th = 0.6
+    mats = MATS + [np.eye(3), np.array([[np.cos(th), -np.sin(th), 80], [np.sin(th), np.cos(th), -40], [0, 0, 1.0]]),
+                   np.array([[0.3, 0, 0], [0, 0.3, 0], [0, 0, 1.0]]), np.array([[3.0, 0, -100], [0, 3.0, -50], [0, 0, 1.0]])]
+    for shape in ((96, 128), (200, 328), (64, 1024)):
+        img = _img(dt, shape, 4)
+        for M in mats:
+            for dsize in ((shape[1], shape[0]), (77, 33)):
+                ref = cv2.warpPerspective(img, M, dsize, flags=flag, borderValue=3.0)
+                got = eng.warp_perspective(_dev(img), M, dsize, interp, False, 3.0).cpu().numpy()
+                assert np.array_equal(got, ref), (shape, dsize, M)
+    frames = np.stack([_img(dt, (96, 256), s) for s in range(11)])       # more frames than pipeline stages
+    got = eng.warp_perspective(_dev(frames), MATS[0], (256, 96), interp).cpu().numpy()
+    for i in range(11):
+        assert np.array_equal(got[i], cv2.warpPerspective(frames[i], MATS[0], (256, 96), flags=flag))
 
 
 def test_perspective_correction_api_golden():
