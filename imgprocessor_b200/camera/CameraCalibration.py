@@ -46,6 +46,20 @@ def _getFromDate(entries, date):
     return entries[0] if i == -1 else entries[i]
 
 
+class _BoundedNLF(object):
+    """NoiseLevelFunction.boundedFunction(x, minY, ax, ay) (camera/NoiseLevelFunction.py:94-107) with its parameters
+    kept, so that kernel K4 can evaluate it per pixel; calling it evaluates the same expression with numpy."""
+
+    def __init__(self, minY, ax, ay):
+        self.coeff = (minY, ax, ay)
+
+    def __call__(self, x):
+        minY, ax, ay = self.coeff
+        with np.errstate(invalid='ignore'):
+            y = ay * (x - ax) ** 0.5
+        return np.maximum(np.nan_to_num(y), minY)
+
+
 class CameraCalibration(object):
     ftype = '.cal'
 
@@ -288,9 +302,10 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         if bgImages is not None:
             if type(bgImages) in (list, tuple) or (isinstance(bgImages, np.ndarray) and bgImages.ndim == 3):
                 if len(bgImages) > 1:
-                    raise NotImplementedError('averaging several background images (single-time-effect removal) '
-                                              'is outside the GPU path; pass one background image')
-                bg = imread(bgImages[0])
+                    # several background images: STE-free average (:488-494), kernel K4
+                    bg = self._ste_average(bgImages, self._nlf_coeff(None))
+                else:
+                    bg = imread(bgImages[0])
             else:
                 bg = imread(bgImages)
             entry = None
@@ -339,23 +354,56 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
             print('Error: %s' % errm)
         return flags
 
+    # ------------------------------------------------------------------ single-time-effect removal (K4)
+    def _nlf_coeff(self, date):
+        """(minY, ax, ay) of NoiseLevelFunction.boundedFunction: the 'noise' calibration entry (:392-397), or what an
+        earlier call stored.  The reference otherwise ESTIMATES a noise level function from the images (oneImageNLF,
+        a host-side histogram fit through the absent fancytools) — not reproduced."""
+        if self.noise_level_function is None:
+            n = self.coeffs['noise']
+            if len(n):
+                coeff = tuple(float(v) for v in _getFromDate(n, date)[2])
+                self.noise_level_function = _BoundedNLF(*coeff)
+        nlf = self.noise_level_function
+        if nlf is None:
+            raise NotImplementedError('single-time-effect removal without a noise calibration needs oneImageNLF '
+                                      '(host-side estimation, not on the GPU path); call addNoise((minY, ax, ay)) first')
+        if not isinstance(nlf, _BoundedNLF):
+            raise NotImplementedError('an arbitrary Python noise_level_function cannot run on the GPU; use '
+                                      'addNoise((minY, ax, ay)) (NoiseLevelFunction.boundedFunction parameters)')
+        return nlf.coeff
+
+    def _ste_average(self, images, coeff, n_std=4):
+        """SingleTimeEffectDetection(images, nStd=4, noise_level_function=nlf).noSTE (:401-403, 491-494) -> float64"""
+        frames = [imread(i, 'gray') for i in images]
+        if any(f.ndim != 2 or f.shape != frames[0].shape for f in frames):
+            raise ValueError('single-time-effect removal needs 2-D frames of one shape')
+        dt = np.result_type(*[f.dtype for f in frames])
+        if dt.type not in (np.uint8, np.uint16, np.float32, np.float64):
+            dt = np.dtype(np.float64)
+        stack = np.stack([np.asarray(f, dtype=dt.newbyteorder('=')) for f in frames])
+        eng = _engine.get_engine(*stack.shape[1:])
+        tt = _engine.torch()
+        return eng.ste_average(tt.from_numpy(stack).to(eng.device), coeff, n_std).cpu().numpy()
+
     # ------------------------------------------------------------------ THE hot path
     def correct(self, images, bgImages=None, exposure_time=None, light_spectrum=None, threshold=0.1, keep_size=True,
                 date=None, deblur=False, denoise=False):
         """Correct one frame: dark current, flat field, 3x3 median-threshold artefact removal, lens
         distortion.  Same arguments and return value (a new float64 array; the input is never modified)
-        as the reference.  Not supported on the GPU path: more than one image per call (the reference
-        averages them after single-time-effect removal) and ``denoise``; ``deblur`` is reported and skipped
-        like any other failing stage."""
+        as the reference.  Several exposures of one scene (list / 3-D array) are first merged into one
+        single-time-effect-free average (kernel K4; needs a 'noise' calibration entry).  Not supported on the GPU
+        path: ``denoise``; ``deblur`` is reported and skipped like any other failing stage."""
         print('CORRECT CAMERA ...')
         date, light_spectrum = self._normalise_args(date, light_spectrum)
         if type(images) in (list, tuple) or (isinstance(images, np.ndarray) and images.ndim == 3
                                              and images.shape[-1] not in (3, 4)):
             if len(images) > 1:
-                raise NotImplementedError(
-                    'correct() with several exposures averages them after single-time-effect removal in the '
-                    'reference; that branch is not on the GPU path. Use correct_batch() for independent frames.')
-            images = images[0]
+                # several exposures of the same scene: one STE-free average (:390-406), kernel K4
+                print('... remove single-time-effects from images ')
+                images = self._ste_average(images, self._nlf_coeff(date['noise']))
+            else:
+                images = images[0]
         image = imread(images)
         if not isinstance(image, np.ndarray) or image.ndim != 2:
             raise ValueError('correct() expects one single-channel 2-D frame')

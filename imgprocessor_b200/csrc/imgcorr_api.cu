@@ -63,6 +63,9 @@ struct imgcorr_ctx {
     double dark_absmax = 0.0, flat_absmin = 1.0;   // over finite entries (flat: non-zero entries)
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
+    double* ste_avg = nullptr;                // K4 scratch: second running-average buffer, thresholds, counts
+    double* ste_thr = nullptr;
+    int* ste_n = nullptr;
     float* warp_tab = nullptr;                // [32][8] Lanczos4 then [32][4] bicubic coefficient tables (K3)
     // host pipeline
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -148,6 +151,9 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->mid[1]);
     cudaFree(c->lens_dev);
     cudaFree(c->warp_tab);
+    cudaFree(c->ste_avg);
+    cudaFree(c->ste_thr);
+    cudaFree(c->ste_n);
     cudaFree(c->dump);
     for (int k = 0; k < 2; ++k) for (auto e : c->prof_ev[k]) cudaEventDestroy(e);
     delete c;
@@ -483,6 +489,50 @@ extern "C" IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* c, const void* src_de
                                      (cudaStream_t)stream, &l);
     c->launches += l;
     if (e != cudaSuccess) return cuda_fail(e, "divide kernel launch");
+    return IMGCORR_OK;
+}
+
+// ---- K4 -------------------------------------------------------------------------------------
+extern "C" IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                                   uint8_t* mask_dev, const double nlf[3], double n_std, void* stream) {
+    GUARD(c);
+    if (!frames_dev || !avg_dev || !nlf) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (dtype < DT_U8 || dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
+    if (n_frames < 2) return fail(IMGCORR_ERR_INVALID, "single-time-effect removal needs at least 2 images (got %d)", n_frames);
+    const size_t npx = (size_t)c->H * c->W;
+    if (!c->ste_avg) {
+        CK(cudaMalloc(&c->ste_avg, npx * sizeof(double)));
+        CK(cudaMalloc(&c->ste_thr, npx * sizeof(double)));
+        CK(cudaMalloc(&c->ste_n, npx * sizeof(int)));
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    // n_frames - 1 launches; ping-pong so that the last one writes avg_dev
+    double* buf[2] = {avg_dev, c->ste_avg};
+    int cur = (n_frames - 2) % 2;                  // buffer the FIRST launch writes
+    K4Args a;
+    a.H = c->H;
+    a.W = c->W;
+    a.thr = c->ste_thr;
+    a.n = c->ste_n;
+    a.mask = mask_dev;
+    a.sc.minY = nlf[0];
+    a.sc.ax = nlf[1];
+    a.sc.ay = nlf[2];
+    a.sc.nstd = n_std;
+    const char* f = (const char*)frames_dev;
+    const size_t fb = npx * dtype_size(dtype);
+    int l = 0;
+    cudaError_t e = cudaSuccess;
+    for (int k = 1; k < n_frames && e == cudaSuccess; ++k) {
+        a.img = k == 1 ? f : f + k * fb;
+        a.img2 = k == 1 ? f + fb : nullptr;
+        a.avg_in = buf[cur ^ 1];
+        a.avg_out = buf[cur];
+        e = launch_k4(a, dtype, st, &l);
+        cur ^= 1;
+    }
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "K4 launch");
     return IMGCORR_OK;
 }
 

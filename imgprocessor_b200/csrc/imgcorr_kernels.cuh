@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include "imgcorr_core.cuh"
 #include "imgcorr_warp.cuh"
+#include "imgcorr_ste.cuh"
 
 namespace imgcorr {
 
@@ -75,5 +76,19 @@ struct K3Args {
 cudaError_t launch_k3(const K3Args& a, int dtype, int interp, int variant, cudaStream_t stream, int* launches);
 cudaError_t launch_k3_divide(const void* src, int dtype, const double* div, double* dst, size_t npx, int n_frames,
                              int sm_count, cudaStream_t stream, int* launches);
+
+// K4: single-time-effect-free average (SingleTimeEffectDetection) ------------------------------
+struct K4Args {
+    const void* img;        // [H][W] the image being added (FIRST: images[0])
+    const void* img2;       // FIRST launch only: images[1]; null for the following images
+    const double* avg_in;   // [H][W] running average (noSTE) before this image (unused by the FIRST launch)
+    double* avg_out;        // [H][W] running average after it (a different buffer: neighbouring tiles read avg_in)
+    double* thr;            // [H][W] threshold = nlf(avg after the first update) * nStd
+    int* n;                 // [H][W] number of values averaged per pixel
+    uint8_t* mask;          // [H][W] accumulated STE mask (save_ste_indices) or null
+    int H, W;
+    SteConst sc;
+};
+cudaError_t launch_k4(const K4Args& a, int dtype, cudaStream_t stream, int* launches);
 
 }  // namespace imgcorr

@@ -287,6 +287,21 @@ class Engine(object):
             int(bool(inverse_map)), float(border_value), self._stream()))
         return out[0] if squeeze else out
 
+    def ste_average(self, frames, nlf, n_std=4.0, want_mask=False):
+        """K4: SingleTimeEffectDetection(frames, nStd=n_std, noise_level_function=boundedFunction(., *nlf)).noSTE
+        for device frames [n,H,W] (n >= 2) -> float64 [H,W] (and the accumulated STE mask if asked)
+        (features/SingleTimeEffectDetection.py:23-75)."""
+        tt = torch()
+        frames = self._frames(frames)
+        n = frames.shape[0]
+        avg = tt.empty((self.H, self.W), dtype=tt.float64, device=self.device)
+        mask = tt.empty((self.H, self.W), dtype=tt.uint8, device=self.device) if want_mask else None
+        coeff = (ctypes.c_double * 3)(*[float(v) for v in nlf])
+        _lib.check(self.lib.imgcorr_ste_average(
+            self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, ctypes.c_void_p(avg.data_ptr()),
+            ctypes.c_void_p(mask.data_ptr()) if want_mask else None, coeff, float(n_std), self._stream()))
+        return (avg, mask.bool()) if want_mask else avg
+
     def undistort_maps(self):
         tt = torch()
         mapx = tt.empty((self.H, self.W), dtype=tt.float32, device=self.device)

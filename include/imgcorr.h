@@ -174,6 +174,18 @@ IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* ctx, const void* src_dev, 
 IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* ctx, const void* src_dev, int src_dtype, const double* divisor_dev, double* dst_dev,
                        size_t pixels_per_frame, int n_frames, void* stream);
 
+/* ---- K4: single-time-effect-free average of several exposures --------------
+ * Replaces SingleTimeEffectDetection(images, nStd, noise_level_function).noSTE in the multi-image branch of
+ * CameraCalibration.correct() (camera/CameraCalibration.py:385-406; features/SingleTimeEffectDetection.py:23-75)
+ * with noise_level_function = NoiseLevelFunction.boundedFunction(x, minY, ax, ay) (camera/NoiseLevelFunction.py:94-107;
+ * nlf[3] = {minY, ax, ay}, the 'noise' calibration entry) and removeSinglePixels (filters/removeSinglePixels.py:4-33).
+ *   frames_dev [n][H][W] of `dtype` (any), n >= 2;  avg_dev [H][W] float64 = noSTE;
+ *   mask_dev   [H][W] uint8 accumulated STE mask (save_ste_indices=True) or NULL.
+ * float64 arithmetic as in the reference; the running mean avg += (x - avg) / n restates fancytools'
+ * MaskedMovingAverage (absent from the reference tree: that ingredient's parity is unpinned, see oracle/ste.py). */
+IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                        uint8_t* mask_dev, const double nlf[3], double n_std, void* stream);
+
 /* page-locked host memory for the *_host entry points */
 IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr);
 IMGCORR_API int imgcorr_host_free(void* ptr);

@@ -9,6 +9,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'host_emul', 'emul.cpp')
 CORE = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_core.cuh')
+STE = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_ste.cuh')
 WARP = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'imgcorr_warp.cuh')
 NET = os.path.join(os.path.dirname(HERE), 'imgprocessor_b200', 'csrc', 'median25_net.inc')
 OUT = os.path.join(HERE, '_build', 'libimgcorr_emul.so')
@@ -20,7 +21,7 @@ def lib():
     global _lib
     if _lib is None:
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
-        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NET), os.path.getmtime(WARP)):
+        if not os.path.exists(OUT) or os.path.getmtime(OUT) < max(os.path.getmtime(SRC), os.path.getmtime(CORE), os.path.getmtime(NET), os.path.getmtime(WARP), os.path.getmtime(STE)):
             subprocess.check_call(['g++', '-O2', '-std=c++17', '-ffp-contract=off', '-fPIC', '-shared',
                                    '-fvisibility=hidden', '-o', OUT, SRC, '-lm'])
         _lib = ctypes.CDLL(OUT)
@@ -92,3 +93,12 @@ def warp(src, M, dsize, interpolation='lanczos4', inverse_map=False, border=0.0)
                         {'lanczos4': 4, 'cubic': 2}[interpolation], int(bool(inverse_map)), ctypes.c_double(border))
     assert r == 0
     return dst
+
+
+def ste(frames, nlf, n_std=4.0, want_mask=False):
+    frames = np.ascontiguousarray(frames, np.float64)
+    n, H, W = frames.shape
+    avg = np.empty((H, W), np.float64)
+    mask = np.zeros((H, W), np.uint8) if want_mask else None
+    lib().emul_ste(_p(frames), n, H, W, _p(np.ascontiguousarray(nlf, np.float64)), ctypes.c_double(n_std), _p(avg), _p(mask))
+    return (avg, mask.astype(bool)) if want_mask else avg

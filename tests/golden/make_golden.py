@@ -217,9 +217,73 @@ def perspective():
     save('perspective', scene=scene, quad=quad[[2, 0, 3, 1]], new_size=np.array(new_size), border=np.int64(4), Hm=Hm, log=np.array(log), **out)
 
 
+def ste():
+    """the reference's SingleTimeEffectDetection / removeSinglePixels / boundedFunction, unmodified,
+    with the restated MaskedMovingAverage injected (ref_shim.install_masked_moving_average)."""
+    ref_shim.install_masked_moving_average()
+    import importlib
+    import imgProcessor.features.SingleTimeEffectDetection as stemod
+    importlib.reload(stemod)
+    from imgProcessor.filters.removeSinglePixels import removeSinglePixels
+    from imgProcessor.camera import NoiseLevelFunction
+    rng = np.random.default_rng(31)
+    H, W = 72, 100
+    base = synth.scene(H, W, seed=5, dtype=np.float64, full_scale=4000.0, hot_dead=False)
+    nlf = (6.0, 20.0, 0.9)                                        # minY, ax, ay
+    frames = []
+    for i in range(5):
+        f = base + rng.normal(0, 1, (H, W)) * NoiseLevelFunction.boundedFunction(base, *nlf)
+        for k in range(6):                                        # cosmic-ray-like blobs and single pixels
+            y, x = rng.integers(2, H - 3), rng.integers(2, W - 3)
+            f[y:y + rng.integers(1, 4), x:x + rng.integers(1, 4)] += rng.uniform(300, 3000)
+        f[rng.random((H, W)) < 2e-3] += 2000.0
+        frames.append(np.clip(np.rint(f), 0, 65535).astype(np.uint16))
+    frames = np.stack(frames)
+    fn = lambda x: NoiseLevelFunction.boundedFunction(x, *nlf)
+    out = {}
+    for n in (2, 3, 5):
+        det = stemod.SingleTimeEffectDetection(list(frames[:n]), nStd=4, noise_level_function=fn, save_ste_indices=True)
+        out['noSTE_%d' % n] = det.noSTE
+        out['mask_%d' % n] = det.mask_STE
+    det = stemod.SingleTimeEffectDetection(list(frames.astype(np.float32)), nStd=3, noise_level_function=fn)
+    out['noSTE_f32_nstd3'] = det.noSTE
+    m = rng.random((64, 80)) > 0.93
+    m[0, 0] = m[63, 79] = m[0, 79] = True
+    m2 = m.copy()
+    removeSinglePixels(m2)
+    xs = np.concatenate([np.linspace(-50, 5000, 301), [np.nan, np.inf, -np.inf, 20.0]])
+    # the multi-image branches of correct() itself (CameraCalibration.py:385-406, 484-498)
+    import imgProcessor.camera.CameraCalibration as calmod
+    calmod.SingleTimeEffectDetection = stemod.SingleTimeEffectDetection
+    dark = synth.dark_map(H, W)
+    flat = synth.flat_map(H, W, p_zero=2e-3)
+    params = synth.lens_moderate(H, W)
+    cal = calmod.CameraCalibration()
+    cal.addDarkCurrent(dark)
+    cal.addFlatField(flat)
+    cal.addLens(make_lens(params, (H, W)))
+    cal.addNoise(nlf)
+    out['correct_3'], out['correct_3_log'] = quiet(cal.correct, list(frames[:3]), threshold=0.1)
+    out['correct_3_log'] = np.array(out['correct_3_log'])
+    bgs = np.stack([np.clip(np.rint(dark + rng.normal(0, 3, (H, W))), 0, 65535) for i in range(3)]).astype(np.uint16)
+    bgs[1, 10:12, 20:23] += 900
+    cal2 = calmod.CameraCalibration()
+    cal2.addFlatField(flat)
+    cal2.addNoise(nlf)
+    cal2.noise_level_function = fn
+    out['correct_bg3'], lg = quiet(cal2.correct, frames[0], bgImages=list(bgs), threshold=0.1)
+    out['correct_bg3_log'] = np.array(lg)
+    out['correct_bg3_bg'] = cal2.temp['bg']
+    save('ste', dark=dark, flat=flat, K=synth.camera_matrix(params), dist=synth.dist_coeffs(params), bgs=bgs, frames=frames, nlf=np.array(nlf), rsp_in=m, rsp_out=m2, bf_x=xs,
+         bf_y=NoiseLevelFunction.boundedFunction(xs, *nlf), **out)
+
+
 if __name__ == '__main__':
     if sys.argv[1:] == ['perspective']:
         perspective()
+    elif sys.argv[1:] == ['ste']:
+        ste()
     else:
         main()
         perspective()
+        ste()

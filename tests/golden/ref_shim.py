@@ -53,3 +53,11 @@ def install_perspective_stubs():
     mod('fancytools.math.Point3D', Point3D=None)
     mod('fancytools.math.vector3d', vectorAngle=None)
     sys.modules['fancytools.math'].line = mod('fancytools.math.line')
+
+
+def install_masked_moving_average():
+    """features/SingleTimeEffectDetection.py:10 imports fancytools.math.MaskedMovingAverage, which is
+    absent.  Inject the restatement of its published algorithm (oracle/ste.py — the one ingredient of the STE
+    branch whose parity stays unpinned) so that the reference's own STE code can be executed unmodified."""
+    from oracle.ste import MaskedMovingAverage
+    sys.modules['fancytools.math.MaskedMovingAverage'].MaskedMovingAverage = MaskedMovingAverage

@@ -174,3 +174,41 @@ int emul_warp(const void* src, int dtype, void* dst, int H, int W, int dh, int d
 #undef GO
     return 0;
 }
+
+// ---- single-time-effect-free average (imgcorr_ste.cuh) ---------------------------------
+#include "../../imgprocessor_b200/csrc/imgcorr_ste.cuh"
+
+// frames: [n][H][W] float64 (the caller widens); avg out [H][W]; mask out [H][W] or null
+extern "C" __attribute__((visibility("default")))
+void emul_ste(const double* frames, int n, int H, int W, const double* nlf, double nstd, double* avg, uint8_t* mask) {
+    SteConst sc{nlf[0], nlf[1], nlf[2], nstd};
+    const size_t npx = (size_t)H * W;
+    std::vector<double> thr(npx), img(npx);
+    std::vector<int> cnt(npx, 1);
+    std::vector<uint8_t> f(npx);
+    for (size_t i = 0; i < npx; ++i) {
+        const double p = frames[i], q = frames[npx + i];
+        avg[i] = (p != p || q != q) ? p + q : (p < q ? p : q);
+        img[i] = (p != p || q != q) ? p + q : (p < q ? q : p);
+        thr[i] = ste_threshold(sc, avg[i]);
+        if (mask) mask[i] = 0;
+    }
+    for (int k = 1; k < n; ++k) {
+        if (k > 1) for (size_t i = 0; i < npx; ++i) img[i] = frames[(size_t)k * npx + i];
+        for (size_t i = 0; i < npx; ++i) f[i] = ste_flag(img[i], avg[i], thr[i]);
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const size_t i = (size_t)y * W + x;
+                bool s = f[i];
+                if (s) {
+                    int nb = 0;
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx)
+                            if ((dy || dx) && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) nb += f[(size_t)(y + dy) * W + x + dx];
+                    s = nb > 0;
+                }
+                if (!s) { cnt[i] += 1; avg[i] = ste_update(img[i], avg[i], cnt[i]); }
+                else if (mask) mask[i] = 1;
+            }
+    }
+}
