@@ -33,4 +33,14 @@ IC_HD bool ste_flag(double img, double avg, double thr) { return dsub(img, avg) 
 // MaskedMovingAverage.update(image, clean) for one clean pixel: n += 1; avg += (image - avg) / n
 IC_HD double ste_update(double img, double avg, int n_new) { return dadd(avg, ddiv(dsub(img, avg), (double)n_new)); }
 
+// Same value, cheaper: for uint8 / uint16 / float32 exposures the numerator is float32-derived (|img - avg| <= ~7e38,
+// and a non-zero difference of such values is >= 1e-61), the divisor a small integer, so the branch-free division of
+// imgcorr_core.cuh applies; non-finite numerators and float64 exposures take the IEEE division.
+template <bool F32RANGE>
+IC_HD double ste_update_fast(double img, double avg, int n_new) {
+    const double d = dsub(img, avg);
+    if (F32RANGE && fabs(d) <= 1e300) return dadd(avg, ddiv_f32range(d, (double)n_new));
+    return dadd(avg, ddiv(d, (double)n_new));
+}
+
 }  // namespace imgcorr

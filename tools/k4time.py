@@ -7,7 +7,9 @@ H, W = 3000, 4096
 e = engine.Engine(H, W, 0)
 res = []
 for n in (2, 4, 8):
-    fr = (torch.rand((n, H, W), device='cuda') * 3000 + 500).to(torch.uint16)
+    base = torch.rand((H, W), device='cuda') * 3000 + 500
+    fr = (base[None] + torch.randn((n, H, W), device='cuda') * 0.5 * base.sqrt()[None]
+          + (torch.rand((n, H, W), device='cuda') < 1e-3) * 3000).clamp(0, 65535).to(torch.uint16)
     for i in range(2): e.ste_average(fr, (5.0, 0.0, 0.5), 4)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(9)]
