@@ -384,7 +384,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         stack = np.stack([np.asarray(f, dtype=dt.newbyteorder('=')) for f in frames])
         eng = _engine.get_engine(*stack.shape[1:])
         tt = _engine.torch()
-        return eng.ste_average(tt.from_numpy(stack).to(eng.device), coeff, n_std).cpu().numpy()
+        return _engine.to_numpy(eng.ste_average(tt.from_numpy(stack).to(eng.device), coeff, n_std))
 
     # ------------------------------------------------------------------ THE hot path
     def correct(self, images, bgImages=None, exposure_time=None, light_spectrum=None, threshold=0.1, keep_size=True,
@@ -448,7 +448,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         with eng.ingest(big_endian, 0):
             out = eng.correct_batch(dev, threshold=threshold if threshold > 0 else 0.0, ksize=3, flags=flags,
                                     use_lens=bool(lens), window=window, out_dtype=tt.float64)
-        result = out.cpu().numpy()
+        result = _engine.to_numpy(out)
         print('DONE')
         return result
 
@@ -463,7 +463,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         eng = _engine.get_engine(*raw.shape)
         dev = tt.from_numpy(np.ascontiguousarray(raw)).to(eng.device)
         out, _ = eng.pointwise_median(dev, 0.0, 0, flags=flags & ~_lib.DO_NAN_TO_NUM, out_dtype=tt.float64)
-        return out.cpu().numpy()
+        return _engine.to_numpy(out)
 
     # ------------------------------------------------------------------ batches of independent frames
     def correct_batch(self, frames, bgImages=None, exposure_time=None, light_spectrum=None, threshold=0.1,

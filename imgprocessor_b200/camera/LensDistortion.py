@@ -109,7 +109,7 @@ class LensDistortion(object):
         dev, _ = _as_device_frame(eng, image)
         window = None if keepSize else tuple(int(v) for v in self.roi)
         out = eng.undistort(dev, border_value=float(borderValue), window=window)
-        self.img = out if is_tensor else out.cpu().numpy()
+        self.img = out if is_tensor else _engine.to_numpy(out)
         return self.img
 
     def distortImage(self, image):
@@ -121,7 +121,7 @@ class LensDistortion(object):
         tt = _engine.torch()
         dev, is_tensor = _as_device_frame(eng, image)
         out = eng.remap(dev, tt.from_numpy(mapx), tt.from_numpy(mapy), 0.0)
-        return out if is_tensor else out.cpu().numpy()
+        return out if is_tensor else _engine.to_numpy(out)
 
     # ------------------------------------------------------------------ map-derived helpers (:382-418)
     def getDistortRectifyMap(self, sizex, sizey):

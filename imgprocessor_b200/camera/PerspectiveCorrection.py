@@ -165,7 +165,7 @@ class PerspectiveCorrection(object):
         if divide_by is not None:
             divide_by = tt.from_numpy(np.ascontiguousarray(divide_by, np.float64))
         out = eng.warp_perspective(img, self.homography, dsize, interpolation, inverse_map, border_value, divide_by)
-        return out if is_tensor else out.cpu().numpy()
+        return out if is_tensor else _engine.to_numpy(out)
 
     def correct(self, img):
         """perspective transformation [after the tilt-factor division] (:380-406)"""

@@ -4,6 +4,7 @@ torch is plumbing only: it owns device memory and streams; every kernel that run
 hand-written sm_100a kernels in csrc/, reached through the C ABI of include/imgcorr.h.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -379,6 +380,38 @@ def pinned_empty(shape, dtype):
     buf._owner = _Owner(p)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr
+
+
+_STAGE = {}
+
+
+def to_numpy(t, threads=8):
+    """device tensor -> new numpy array.  Large results go through a cached page-locked staging tensor and a
+    multi-threaded copy into the fresh array: `tensor.cpu()` spends ~45 ms on the page faults of a 98 MB float64
+    frame (4096x3000), this takes ~6 ms.  The array returned is ordinary pageable memory owned by the caller."""
+    tt = torch()
+    nbytes = t.numel() * t.element_size()
+    if not t.is_cuda or nbytes < (16 << 20):
+        return t.cpu().numpy()
+    t = t.contiguous()
+    key = (t.dtype, t.device.index)
+    stage = _STAGE.get(key)
+    if stage is None or stage.numel() < t.numel():
+        stage = _STAGE[key] = tt.empty(t.numel(), dtype=t.dtype, pin_memory=True)
+    view = stage[:t.numel()].view(t.shape)
+    view.copy_(t)                                  # synchronous for a pinned destination
+    src = view.numpy()
+    out = np.empty(src.shape, src.dtype)
+    flat_src, flat_out = src.reshape(-1), out.reshape(-1)
+    import threading
+    n = max(1, min(int(threads), os.cpu_count() or 1, nbytes >> 23))      # one thread per 8 MB
+    cuts = np.linspace(0, flat_src.size, n + 1).astype(np.int64)
+    workers = [threading.Thread(target=np.copyto, args=(flat_out[a:b], flat_src[a:b])) for a, b in zip(cuts[:-1], cuts[1:])]
+    for w in workers:
+        w.start()
+    for w in workers:
+        w.join()
+    return out
 
 
 _ENGINES = {}

@@ -41,7 +41,7 @@ def medianThreshold(img, threshold=0.1, size=3, condition='>', copy=True):
     eng = _engine.get_engine(img.shape[0], img.shape[1])
     dev = tt.from_numpy(np.ascontiguousarray(img)).to(eng.device)
     out, ind = eng.pointwise_median(dev, threshold, size, condition, flags=0, out_dtype=dev.dtype, want_mask=True)
-    res = out.cpu().numpy()
+    res = _engine.to_numpy(out)
     indices = ind.cpu().numpy().astype(bool)
     if copy:
         return res, indices

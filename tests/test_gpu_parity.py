@@ -603,3 +603,16 @@ def test_config4_f32_5x5_strong_lens(ip):
     ref = refpath.lens_correct(want, synth.camera_matrix(p), synth.dist_coeffs(p), keep_size=True)
     assert (out != ref).mean() < 1e-6          # analytic map vs cv2's: at most a stray 1/32-px flip
     assert np.abs(out - ref).max() / 4095.0 < 1e-3
+
+
+def test_to_numpy_staged_copy(ip):
+    """engine.to_numpy (pinned staging + threaded copy for large results) returns exactly tensor.cpu().numpy()"""
+    for shape, dt in (((3000, 4096), torch.float64), ((5, 700, 900), torch.float32), ((1200, 1100), torch.uint16),
+                      ((10, 10), torch.float64), ((2049, 1025), torch.uint8)):
+        t = (torch.rand(shape, device='cuda') * 200).to(dt)
+        a = ip.engine_mod.to_numpy(t)
+        assert a.flags.writeable and np.array_equal(a, t.cpu().numpy())
+    t = torch.rand((2000, 3000), device='cuda', dtype=torch.float64)[:, ::2]          # non-contiguous view
+    assert np.array_equal(ip.engine_mod.to_numpy(t), t.cpu().numpy())
+    b = ip.engine_mod.to_numpy(torch.zeros((1500, 1500), device='cuda', dtype=torch.float64))   # staging reuse must not alias
+    assert not b.any() and a.any()
