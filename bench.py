@@ -231,6 +231,7 @@ def run_ours(args):
     eng.set_lens(Kmat, dvec, P)
     eng.set_option(_lib.OPT_CHAIN_GROUP, args.group)
 
+    numa = {'bound': False} if os.environ.get('IMGCORR_NO_NUMA_BIND') else sharding.bind_host_to_gpu(local)
     raw = synth.scene_torch(F, H, W, 1000 + rank, dev, 'uint16')
     out = torch.empty((F, H, W), dtype=torch.float32, device=dev)
     px_step = float(F) * H * W
@@ -306,7 +307,8 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'Mpx/s', 'h2d_bytes_per_step': int(reps * pool * H * W * 2),
                     'd2h_bytes_per_step': int(reps * pool * H * W * 4), 'frames_per_step_per_gpu': reps * pool,
                     'steps': e2e_steps, 'pinned_pool_frames': pool, 'checksum': checksum,
-                    'api': 'imgcorr_correct_host (C ABI) with pinned host buffers; copies inside the timed region'},
+                    'api': 'imgcorr_correct_host (C ABI) with pinned host buffers; copies inside the timed region',
+                    'host_numa_binding': numa},
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'kernel': 'K1 k1_stream_kernel (fused dark/flat/nan_to_num/3x3 median-threshold)',
                          'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': args.k1_traffic,

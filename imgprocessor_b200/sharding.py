@@ -70,3 +70,46 @@ def reduce_sum(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or 'cpu')
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
+
+
+def parse_cpulist(text):
+    """'0-3,8,10-11' -> [0, 1, 2, 3, 8, 10, 11] (the format of sysfs local_cpulist)"""
+    cpus = []
+    for part in text.strip().split(','):
+        if not part:
+            continue
+        if '-' in part:
+            a, b = part.split('-')
+            cpus.extend(range(int(a), int(b) + 1))
+        else:
+            cpus.append(int(part))
+    return cpus
+
+
+def bind_host_to_gpu(device_index, sysfs='/sys/bus/pci/devices'):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs local_cpulist of the GPU's PCI
+    function), so that the page-locked staging buffers allocated afterwards are node-local: with one process per
+    GPU the host<->device streams of the ranks then do not all cross the same socket interconnect.  Returns a
+    dict describing what was done; never raises (a box without the sysfs entries is left as it is)."""
+    import os
+    info = {'bound': False}
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = '%04x:%02x:%02x.0' % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        info['pci'] = bdf
+        with open(os.path.join(sysfs, bdf, 'local_cpulist')) as f:
+            cpus = parse_cpulist(f.read())
+        try:
+            with open(os.path.join(sysfs, bdf, 'numa_node')) as f:
+                info['numa_node'] = int(f.read().strip())
+        except (OSError, ValueError):
+            pass
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed and len(allowed) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, allowed)
+            info['bound'] = True
+        info['cpus'] = len(allowed)
+    except Exception as e:                      # noqa: BLE001 - best effort by design
+        info['error'] = '%s: %s' % (type(e).__name__, e)
+    return info

@@ -82,3 +82,14 @@ def test_lens_calibration_host_side():
     assert c['reprojectionError'] < 1e-2
     assert np.allclose(c['cameraMatrix'], K, rtol=2e-3, atol=1.0)
     assert np.allclose(np.ravel(c['distortionCoeffs'])[:2], dist[:2], atol=2e-2)
+
+
+def test_parse_cpulist_and_numa_binding(tmp_path, monkeypatch):
+    from imgprocessor_b200 import sharding
+    assert sharding.parse_cpulist('0-3,8,10-11\n') == [0, 1, 2, 3, 8, 10, 11]
+    assert sharding.parse_cpulist('') == []
+    # without a CUDA device the binding reports the failure and leaves the process alone
+    import os
+    before = os.sched_getaffinity(0)
+    info = sharding.bind_host_to_gpu(0, sysfs=str(tmp_path))
+    assert info['bound'] is False and os.sched_getaffinity(0) == before
