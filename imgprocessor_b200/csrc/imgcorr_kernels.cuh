@@ -40,6 +40,8 @@ cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant
 bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
+bool k1_stream5_eligible(const K1Args& a, int raw_dtype, int out_dtype);     // 5x5 streaming pipeline
+cudaError_t launch_k1_stream5(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 bool k1_stream2_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 cudaError_t launch_k1_stream2(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 

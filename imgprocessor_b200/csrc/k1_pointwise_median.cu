@@ -469,10 +469,15 @@ cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant
         return launch_k1_stream2(a, raw_dtype, out_dtype, sm_count, seg_rows, st);
     }
     const bool stream_ok = (variant == 0 || variant == 3) && k1_stream_eligible(a, raw_dtype, out_dtype);
-    if (variant == 3 && !stream_ok) return cudaErrorNotSupported;
+    const bool stream5_ok = (variant == 0 || variant == 3) && k1_stream5_eligible(a, raw_dtype, out_dtype);
+    if (variant == 3 && !stream_ok && !stream5_ok) return cudaErrorNotSupported;
     if (stream_ok) {
         if (launches) ++*launches;
         return launch_k1_stream(a, raw_dtype, out_dtype, sm_count, seg_rows, st);
+    }
+    if (stream5_ok) {
+        if (launches) ++*launches;
+        return launch_k1_stream5(a, raw_dtype, out_dtype, sm_count, seg_rows, st);
     }
     bool tma = variant != 1 && k1_tma_eligible(a, raw_dtype, out_dtype);
     if (variant == 2 && !tma) return cudaErrorNotSupported;

@@ -171,6 +171,70 @@ def test_k1_stream_segment_seams(ip, seg_rows):
     e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
 
 
+@pytest.mark.parametrize('seg_rows', [0, 8, 9, 11, 16, 37, 1000])
+@pytest.mark.parametrize('shape', [(8, 16), (75, 256), (37, 112), (64, 120), (130, 344)])
+def test_k1_stream5_bit_exact(ip, seg_rows, shape):
+    """the 5x5 streaming kernel: segment seams at any height (incl. heights that leave a 1-row tail, which the launcher
+    avoids), strip edges at non-multiples of 112 columns, top / bottom / left / right 'reflect', every instantiation"""
+    H, W = shape
+    raw, dark, flat = _case(H, W, 16, np.uint16)
+    e = _eng(ip, H, W, 3)                      # variant 3 = streaming pipeline or an error: never a silent tile fallback
+    e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, seg_rows)
+    try:
+        e.set_dark(dark)
+        e.set_flat(flat)
+        out, _ = e.pointwise_median(_dev(raw), 0.1, 5)                                  # chain instantiation
+        want, _ = models.median_threshold_model(models.pointwise_model(raw, dark, flat, True), 0.1, 5)
+        assert np.array_equal(out.cpu().numpy(), want)
+        rawf = synth.scene(H, W, 17, np.float32)
+        out, mask = e.pointwise_median(_dev(rawf), 0.1, 5, want_mask=True)              # float32 frames: checked instantiation
+        want, wmask = models.median_threshold_model(models.pointwise_model(rawf, dark, flat, True), 0.1, 5)
+        assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+        flat2, dark2 = flat.copy(), dark.copy()
+        flat2[min(7, H - 1), 9], flat2[min(8, H - 1), 9], dark2[H // 2, W // 2] = np.inf, np.nan, -np.inf
+        e.set_dark(dark2)
+        e.set_flat(flat2)
+        for cond in ('>', '<'):                                                         # run-time-flag instantiation
+            out, mask = e.pointwise_median(_dev(raw), 0.1, 5, cond, want_mask=True)
+            want, wmask = models.median_threshold_model(models.pointwise_model(raw, dark2, flat2, True), 0.1, 5, cond)
+            assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+        # direct medianThreshold on the image dtype (no calibration): uint16 -> uint16 and uint8 -> uint8 with mask
+        e.set_dark(None)
+        e.set_flat(None)
+        for dt in (np.uint16, np.uint8) if W % 16 == 0 else (np.uint16,):
+            img = synth.scene(H, W, 18, dt)
+            out, mask = e.pointwise_median(_dev(img), 0.1, 5, flags=0, out_dtype=_dev(img).dtype, want_mask=True)
+            want, wmask = models.median_threshold_model(img, 0.1, 5)
+            assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    finally:
+        e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, 0)
+        e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
+def test_k1_stream5_batch_and_guard_band(ip):
+    H, W, n = 70, 272, 5
+    e = _eng(ip, H, W, 3)
+    _, dark, flat = _case(H, W, 1)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    frames = np.stack([synth.scene(H, W, 30 + i, np.uint16) for i in range(n)])
+    out, mask = e.pointwise_median(_dev(frames), 0.1, 5, want_mask=True)
+    for i in range(n):
+        want, wmask = models.median_threshold_model(models.pointwise_model(frames[i], dark, flat, True), 0.1, 5)
+        assert np.array_equal(out[i].cpu().numpy(), want) and np.array_equal(mask[i].cpu().numpy().astype(bool), wmask)
+    # pixels engineered onto the threshold from both sides: the float32 guard band must hand them to the exact path
+    e.set_dark(None)
+    e.set_flat(None)
+    rng = np.random.default_rng(5)
+    img = np.full((H, W), 1000.0, np.float32) + rng.random((H, W)).astype(np.float32)
+    ys, xs = rng.integers(3, H - 3, 200), rng.integers(3, W - 3, 200)
+    img[ys, xs] = np.float32(1100.0) * (1 + rng.integers(-4, 5, 200).astype(np.float32) * np.float32(2.0 ** -23))
+    out, mask = e.pointwise_median(_dev(img), 0.1, 5, flags=0, want_mask=True)
+    want, wmask = models.median_threshold_model(img, 0.1, 5)
+    assert np.array_equal(out.cpu().numpy(), want) and np.array_equal(mask.cpu().numpy().astype(bool), wmask)
+    e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
 def test_k1_multi_frame_batch(ip):
     H, W, n = 70, 272, 5
     e = _eng(ip, H, W, 0)

@@ -11,5 +11,5 @@ raw = synth.scene_torch(4, H, W, 7, torch.device('cuda', 0), 'uint16')
 out = torch.empty((1, H, W), dtype=torch.float32, device='cuda')
 e.set_option(_lib.OPT_K1_VARIANT, variant); e.set_option(_lib.OPT_K1_SEG_ROWS, seg)
 for i in range(6):
-    e.pointwise_median(raw[i % 4], 0.1, 3, out=out)
+    e.pointwise_median(raw[i % 4], 0.1, int(os.environ.get("KSIZE", "3")), out=out)
 torch.cuda.synchronize()
