@@ -332,7 +332,9 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     const long long slots = (long long)sm_count * per_sm[slot];
     if (seg_rows <= 0) {
         // all units cost the same: pick the segment height whose unit count fills whole waves of the resident CTAs best,
-        // counting the two re-read halo rows per segment against it
+        // counting the two re-read halo rows per segment against it.  (Searching beyond 8 waves finds better fills on
+        // paper — 231-row segments for 32 frames — but measured slower, 36.1 vs 33.6 us/frame: every unit start refills
+        // the pipeline and runs its first chunk row by row.)
         double best = -1.0;
         for (int waves = 1; waves <= 8; ++waves) {
             long long segs_try = slots * waves / ((long long)strips * a.n_frames);
