@@ -230,6 +230,7 @@ def run_ours(args):
         eng.set_flat(synth.flat_map(H, W))
     eng.set_lens(Kmat, dvec, P)
     eng.set_option(_lib.OPT_CHAIN_GROUP, args.group)
+    eng.set_option(_lib.OPT_CHAIN_OVERLAP, int(args.overlap))
 
     numa = {'bound': False} if os.environ.get('IMGCORR_NO_NUMA_BIND') else sharding.bind_host_to_gpu(local)
     raw = synth.scene_torch(F, H, W, 1000 + rank, dev, 'uint16')
@@ -336,6 +337,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--frames', type=int, default=256, help='frames per GPU per step')
     ap.add_argument('--group', type=int, default=32, help='frames per K1/K2 launch inside the chain')
+    ap.add_argument('--overlap', type=int, default=0, help='1: K1 of the next group overlaps K2 of the current one')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-pool', type=int, default=32, help='pinned host frames cycled by the end-to-end leg')
     ap.add_argument('--e2e-steps', type=int, default=3)

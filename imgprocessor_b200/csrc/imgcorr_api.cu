@@ -63,6 +63,9 @@ struct imgcorr_ctx {
     double dark_absmax = 0.0, flat_absmin = 1.0;   // over finite entries (flat: non-zero entries)
     long long launches = 0;
     float* mid[2] = {nullptr, nullptr};
+    int chain_overlap = 0;
+    cudaStream_t s_chain = nullptr;           // high-priority stream of K1 in overlap mode
+    cudaEvent_t ev_k1[2] = {nullptr, nullptr}, ev_k2[2] = {nullptr, nullptr}, ev_entry = nullptr;
     double* ste_avg = nullptr;                // K4 scratch: second running-average buffer, thresholds, counts
     double* ste_thr = nullptr;
     int* ste_n = nullptr;
@@ -143,6 +146,9 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_k) cudaStreamDestroy(c->s_k);
     if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->s_chain) cudaStreamDestroy(c->s_chain);
+    for (int i = 0; i < 2; ++i) { if (c->ev_k1[i]) cudaEventDestroy(c->ev_k1[i]); if (c->ev_k2[i]) cudaEventDestroy(c->ev_k2[i]); }
+    if (c->ev_entry) cudaEventDestroy(c->ev_entry);
     cudaFree(c->dark);
     cudaFree(c->ascent);
     cudaFree(c->flat);
@@ -169,6 +175,9 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
             c->k2_variant = value;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_CHAIN_OVERLAP:
+            c->chain_overlap = value ? 1 : 0;
             return IMGCORR_OK;
         case IMGCORR_OPT_K3_VARIANT:
             if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k3 variant %d", value);
@@ -567,25 +576,59 @@ static int chain_frames(imgcorr_ctx* c, const void* raw, int raw_dtype, void* ou
         c->mid_frames = grp;
     }
     const size_t out_stride = (size_t)ow * oh * dtype_size(out_dtype);
+    // Overlap mode: K1 of group g+1 runs on an internal high-priority stream while K2 of group g runs on the caller's
+    // stream, so that K2's blocks fill the SM slots K1's last, partially filled wave leaves idle (and vice versa).  The
+    // two scratch buffers are handed back and forth with events; every K2 stays on the caller's stream, so the call is
+    // stream-ordered as before.  A profiled group (IMGCORR_OPT_PROFILE) runs unoverlapped so that its brackets time the
+    // kernel alone.
+    const bool overlap = c->chain_overlap && n > grp;
+    cudaStream_t s1 = st;
+    if (overlap) {
+        if (!c->s_chain) {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&c->s_chain, cudaStreamNonBlocking, hi));
+            for (int i = 0; i < 2; ++i) {
+                CK(cudaEventCreateWithFlags(&c->ev_k1[i], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&c->ev_k2[i], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+        }
+        s1 = c->s_chain;
+        CK(cudaEventRecord(c->ev_entry, st));          // K1 must not start before the caller's earlier work on `st`
+        CK(cudaStreamWaitEvent(s1, c->ev_entry, 0));
+    }
     int gi = 0;
+    bool exclusive_next = false;
     for (int f = 0; f < n; f += grp, ++gi) {
         const int nf = n - f < grp ? n - f : grp;
         float* mid = c->mid[gi & 1];
         const bool prof = c->profile > 0 && (c->chain_groups_seen++ % c->profile) == 0;
         if (prof) { c->prof_frames[0] += nf; c->prof_frames[1] += nf; }
+        if (overlap) {
+            // this buffer was last read by K2 of group gi-2; a profiled group (or the one after it) also waits for gi-1
+            if (gi >= 2) CK(cudaStreamWaitEvent(s1, c->ev_k2[gi & 1], 0));
+            if ((prof || exclusive_next) && gi >= 1) CK(cudaStreamWaitEvent(s1, c->ev_k2[(gi - 1) & 1], 0));
+            exclusive_next = prof;
+        }
         K1Args a;
         int r = fill_k1(c, a, (const char*)raw + f * raw_stride, raw_dtype, mid, nullptr, nf, thr, ksize, IMGCORR_COND_GT, flags);
         if (r) return r;
         int l = 0;
-        if (prof) prof_mark(c, 0, st);
-        cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, c->k1_seg_rows, st, &l);
-        if (prof) prof_mark(c, 0, st);
+        if (prof) prof_mark(c, 0, s1);
+        cudaError_t e = launch_k1(a, raw_dtype, DT_F32, c->k1_variant, c->sm_count, c->k1_seg_rows, s1, &l);
+        if (prof) prof_mark(c, 0, s1);
         c->launches += l;
         if (e != cudaSuccess) return cuda_fail(e, "K1 launch");
+        if (overlap) {
+            CK(cudaEventRecord(c->ev_k1[gi & 1], s1));
+            CK(cudaStreamWaitEvent(st, c->ev_k1[gi & 1], 0));
+        }
         if (prof) prof_mark(c, 1, st);
         r = run_k2(c, mid, DT_F32, (char*)out + f * out_stride, out_dtype, nf, nullptr, nullptr, border, x0, y0, ow, oh, st);
         if (prof) prof_mark(c, 1, st);
         if (r) return r;
+        if (overlap) CK(cudaEventRecord(c->ev_k2[gi & 1], st));
     }
     return IMGCORR_OK;
 }

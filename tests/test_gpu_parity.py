@@ -589,6 +589,32 @@ def test_correct_batch_device_and_host(ip):
     assert r is pin_out and np.array_equal(pin_out.astype(np.float64), single[:, y:y + h, x:x + w])
 
 
+def test_chain_overlap_mode_is_identical(ip):
+    """IMGCORR_OPT_CHAIN_OVERLAP: K1 of group g+1 on the internal high-priority stream while K2 of group g runs — same
+    output for every group size (buffer hand-off by events), with and without profiling brackets"""
+    H, W, n = 96, 128, 11
+    g = load_golden('correct_u16_keep1')
+    cal = _cal(ip, g)
+    frames = _dev(np.stack([synth.scene(H, W, 50 + i, np.uint16) for i in range(n)]))
+    e = ip.engine_mod.get_engine(H, W)
+    _quiet(cal.correct, frames[0].cpu().numpy(), threshold=0.1)            # uploads the calibration into the engine
+    want = e.correct_batch(frames, threshold=0.1).cpu().numpy()
+    try:
+        e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 1)
+        for group in (1, 2, 3, 4, 16):
+            e.set_option(ip.lib_mod.OPT_CHAIN_GROUP, group)
+            for prof in (0, 1, 2):
+                e.set_option(ip.lib_mod.OPT_PROFILE, prof)
+                for rep in range(3):
+                    got = e.correct_batch(frames, threshold=0.1)
+                assert np.array_equal(got.cpu().numpy(), want), (group, prof)
+                e.profile_read()
+    finally:
+        e.set_option(ip.lib_mod.OPT_PROFILE, 0)
+        e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 0)
+        e.set_option(ip.lib_mod.OPT_CHAIN_GROUP, 16)
+
+
 # ---------------------------------------------------------------------------- BASELINE.json sizes
 def test_config1_1024_f32_full_chain(ip):
     """configs[0]: one 1024x1024 float32 frame, dark + flat + 3x3 + 5-coefficient lens, vs the float64
