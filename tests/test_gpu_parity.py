@@ -695,6 +695,35 @@ def test_config4_f32_5x5_strong_lens(ip):
     assert np.abs(out - ref).max() / 4095.0 < 1e-3
 
 
+def test_config5_6000x4000_streamed_from_pinned_pool(ip):
+    """configs[4]: 6000x4000 uint16 frames cycled from a small pool of pinned buffers through the host-buffer chain; the
+    streamed result equals the device-resident chain, and K1 of that chain equals the oracle on a band of rows"""
+    import cv2
+    H, W, pool = 4000, 6000, 3
+    e = ip.engine_mod.get_engine(H, W)
+    dark, flat = synth.dark_map(H, W), synth.flat_map(H, W)
+    e.set_dark(dark)
+    e.set_flat(flat)
+    p = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    P, _ = cv2.getOptimalNewCameraMatrix(K, d, (W, H), 1, (W, H))
+    e.set_lens(K, d, P)
+    src = synth.scene_torch(pool, H, W, 3, torch.device('cuda', 0), 'uint16')
+    h_in = ip.engine_mod.pinned_empty((pool, H, W), np.uint16)
+    h_out = ip.engine_mod.pinned_empty((pool, H, W), np.float32)
+    h_in[...] = src.cpu().numpy()
+    for rep in range(3):                                     # the pool is reused, as the streaming config does
+        h_out[...] = -1
+        e.correct_host(h_in, out=h_out)
+        assert np.array_equal(h_out, e.correct_batch(src).cpu().numpy())
+    k1, _ = e.pointwise_median(src[0], 0.1, 3)
+    rows = slice(1990, 2060)
+    band = slice(rows.start - 1, rows.stop + 1)
+    want, _ = models.median_threshold_model(models.pointwise_model(h_in[0][band], dark[band], flat[band], True), 0.1, 3)
+    assert np.array_equal(k1[rows].cpu().numpy(), want[1:-1])
+    e.set_lens(None, None, None)
+
+
 def test_to_numpy_staged_copy(ip):
     """engine.to_numpy (pinned staging + threaded copy for large results) returns exactly tensor.cpu().numpy()"""
     for shape, dt in (((3000, 4096), torch.float64), ((5, 700, 900), torch.float32), ((1200, 1100), torch.uint16),
