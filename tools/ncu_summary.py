@@ -12,7 +12,8 @@ raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv', '--kernel-name
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, data = rows[0], rows[1], rows[2:]
 idx = {h: i for i, h in enumerate(hdr)}
-r = data[0]
+import os
+r = data[int(os.environ.get('NCU_INDEX', '0'))]
 lines = []
 w = lines.append
 w('ncu --set full --clock-control none  (report: %s, %d launch(es) of the kernel captured; first one shown)' % (rep.split('/')[-1], len(data)))
