@@ -159,8 +159,8 @@ class PerspectiveCorrection(object):
         h, w = img.shape
         eng = _engine.get_engine(h, w)
         if not is_tensor:
-            if img.dtype.type not in (np.uint16, np.float32, np.float64):
-                raise TypeError('unsupported image dtype %s (uint16, float32, float64)' % img.dtype)
+            if img.dtype.type not in (np.uint8, np.uint16, np.float32, np.float64):
+                raise TypeError('unsupported image dtype %s (uint8, uint16, float32, float64)' % img.dtype)
             img = tt.from_numpy(np.ascontiguousarray(img)).to(eng.device)
         if divide_by is not None:
             divide_by = tt.from_numpy(np.ascontiguousarray(divide_by, np.float64))

@@ -69,6 +69,7 @@ struct imgcorr_ctx {
     double* ste_avg = nullptr;                // K4 scratch: second running-average buffer, thresholds, counts
     double* ste_thr = nullptr;
     int* ste_n = nullptr;
+    int16_t* warp_itab[2] = {nullptr, nullptr};   // [bicubic, Lanczos4] fixed-point weights for uint8 images (K3)
     float* warp_tab = nullptr;                // [32][8] Lanczos4 then [32][4] bicubic coefficient tables (K3)
     // host pipeline
     cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
@@ -157,6 +158,8 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->mid[1]);
     cudaFree(c->lens_dev);
     cudaFree(c->warp_tab);
+    cudaFree(c->warp_itab[0]);
+    cudaFree(c->warp_itab[1]);
     cudaFree(c->ste_avg);
     cudaFree(c->ste_thr);
     cudaFree(c->ste_n);
@@ -454,8 +457,7 @@ extern "C" IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* c, const void* 
                                         int interpolation, int inverse_map, double border_value, void* stream) {
     GUARD(c);
     if (!src_dev || !dst_dev || !M) return fail(IMGCORR_ERR_INVALID, "null pointer");
-    if (dtype == DT_U8) return fail(IMGCORR_ERR_INVALID, "warp_perspective: uint8 images are not implemented (OpenCV's int16 fixed-point weights)");
-    if (dtype != DT_U16 && dtype != DT_F32 && dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
+    if (dtype < DT_U8 || dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
     if (interpolation != IMGCORR_INTER_LANCZOS4 && interpolation != IMGCORR_INTER_CUBIC)
         return fail(IMGCORR_ERR_INVALID, "interpolation must be IMGCORR_INTER_LANCZOS4 or IMGCORR_INTER_CUBIC");
     if (src_h <= 0 || src_w <= 0 || dst_h <= 0 || dst_w <= 0 || src_h > 32767 || src_w > 32767 || dst_h > 32767 || dst_w > 32767)
@@ -468,7 +470,19 @@ extern "C" IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* c, const void* 
         CK(cudaMalloc(&c->warp_tab, sizeof(h)));
         CK(cudaMemcpy(c->warp_tab, h, sizeof(h), cudaMemcpyHostToDevice));
     }
+    const int lz = interpolation == IMGCORR_INTER_LANCZOS4;
+    if (dtype == DT_U8 && !c->warp_itab[lz]) {
+        // OpenCV's fixed-point weight table for uint8 images, built on the host once per interpolation
+        const int nn = lz ? 8 : 4;
+        std::vector<float> t(32 * 8);
+        if (lz) warp_lanczos4_table(t.data()); else warp_cubic_table(t.data());
+        std::vector<int16_t> it((size_t)32 * 32 * nn * nn);
+        warp_fixed_table(t.data(), nn, it.data());
+        CK(cudaMalloc(&c->warp_itab[lz], it.size() * sizeof(int16_t)));
+        CK(cudaMemcpy(c->warp_itab[lz], it.data(), it.size() * sizeof(int16_t), cudaMemcpyHostToDevice));
+    }
     K3Args a;
+    a.itab = dtype == DT_U8 ? c->warp_itab[lz] : nullptr;
     a.src = src_dev;
     a.dst = dst_dev;
     a.H = src_h;
@@ -476,7 +490,7 @@ extern "C" IMGCORR_API int imgcorr_warp_perspective(imgcorr_ctx* c, const void* 
     a.dh = dst_h;
     a.dw = dst_w;
     a.n_frames = n_frames;
-    a.border = border_for_dtype(0, dtype == DT_U16, border_value);
+    a.border = border_for_dtype(dtype == DT_U8, dtype == DT_U16, border_value);
     a.wc = make_warp_const(M, inverse_map, dst_w, dst_h);
     a.tab = interpolation == IMGCORR_INTER_LANCZOS4 ? c->warp_tab : c->warp_tab + 32 * 8;
     int l = 0;

@@ -74,6 +74,7 @@ struct K3Args {
     double border;          // already converted to the image dtype's value range
     WarpConst wc;
     const float* tab;       // device coefficient table [32][N] of the interpolation
+    const int16_t* itab;    // uint8 images: device fixed-point weights [32][32][N*N] (null otherwise)
 };
 cudaError_t launch_k3(const K3Args& a, int dtype, int interp, int variant, cudaStream_t stream, int* launches);
 cudaError_t launch_k3_divide(const void* src, int dtype, const double* div, double* dst, size_t npx, int n_frames,

@@ -95,6 +95,37 @@ inline void warp_cubic_table(float* tab) {
     }
 }
 
+// uint8 images: OpenCV's fixed-point branch of initInterTab2D — int16 weights [32][32][n*n] (phase fy, phase fx, tap
+// row-major) = saturate_cast<short>(wy * wx * 2^15), the sum of each phase pair forced to 2^15 on one of the four
+// central taps (the largest if the sum fell short, the smallest if it overshot).
+inline void warp_fixed_table(const float* tab, int n, int16_t* out) {
+    const int k2 = n / 2;
+    for (int i = 0; i < 32; ++i)
+        for (int j = 0; j < 32; ++j) {
+            int16_t* it = out + ((size_t)i * 32 + j) * n * n;
+            int isum = 0;
+            for (int a = 0; a < n; ++a)
+                for (int b = 0; b < n; ++b) {
+                    const float v = tab[i * n + a] * tab[j * n + b];
+                    float r = nearbyintf(v * 32768.0f);
+                    r = r < -32768.0f ? -32768.0f : (r > 32767.0f ? 32767.0f : r);
+                    it[a * n + b] = (int16_t)r;
+                    isum += it[a * n + b];
+                }
+            if (isum != 32768) {
+                const int diff = isum - 32768;
+                int Mk1 = k2, Mk2 = k2, mk1 = k2, mk2 = k2;
+                for (int a = k2; a < k2 + 2; ++a)
+                    for (int b = k2; b < k2 + 2; ++b) {
+                        if (it[a * n + b] < it[mk1 * n + mk2]) { mk1 = a; mk2 = b; }
+                        else if (it[a * n + b] > it[Mk1 * n + Mk2]) { Mk1 = a; Mk2 = b; }
+                    }
+                if (diff < 0) it[Mk1 * n + Mk2] = (int16_t)(it[Mk1 * n + Mk2] - diff);
+                else it[mk1 * n + mk2] = (int16_t)(it[mk1 * n + mk2] - diff);
+            }
+        }
+}
+
 // ---- coordinates --------------------------------------------------------------------------
 #if defined(__CUDA_ARCH__)
 IC_HD int d2i_rn(double v) { return __double2int_rn(v); }
@@ -173,6 +204,35 @@ IC_HD AT warp_pixel(const T* S0, int H, int W, FixedCoord c, const float* tab, A
         return warp_sum_interior<T, AT, N>(S0 + (long long)sy * W + sx, W, wy, wx);
     if (sx >= W || sx + N <= 0 || sy >= H || sy + N <= 0) return cv;
     return warp_sum_border<T, AT, N>(S0, H, W, sx, sy, wy, wx, cv);
+}
+
+// uint8 pixel: w = the n*n int16 weights of this pixel's phase pair; int32 accumulation, FixedPtCast = rounding shift by
+// 15 bits + saturation.  The interior sum and OpenCV's border form  cv*2^15 + sum((S - cv) * w)  are both exact integers.
+template <int N>
+IC_HD uint8_t warp_pixel_u8(const uint8_t* S0, int H, int W, FixedCoord c, const int16_t* w, int cv) {
+    const int off = N / 2 - 1;
+    const int sx = c.ix - off, sy = c.iy - off;
+    int sum;
+    if (sx >= W || sx + N <= 0 || sy >= H || sy + N <= 0) {
+        sum = cv << 15;
+    } else {
+        const int w1 = W - (N - 1) > 0 ? W - (N - 1) : 0, h1 = H - (N - 1) > 0 ? H - (N - 1) : 0;
+        const bool interior = (unsigned)sx < (unsigned)w1 && (unsigned)sy < (unsigned)h1;
+        sum = interior ? 0 : cv << 15;
+        const int sub = interior ? 0 : cv;
+        for (int r = 0; r < N; ++r) {
+            const int yy = sy + r;
+            if (yy < 0 || yy >= H) continue;
+            const uint8_t* R = S0 + (long long)yy * W;
+            for (int k = 0; k < N; ++k) {
+                const int xx = sx + k;
+                if (xx < 0 || xx >= W) continue;
+                sum += ((int)R[xx] - sub) * (int)w[r * N + k];
+            }
+        }
+    }
+    const int v = (sum + (1 << 14)) >> 15;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
 }  // namespace imgcorr

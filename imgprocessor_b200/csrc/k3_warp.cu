@@ -237,6 +237,24 @@ cudaError_t launch_tiled(const K3Args& a, int interp, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// uint8 images (OpenCV's int16 fixed-point weights): one thread per output pixel, the 2-D weight entry of the pixel's
+// phase pair is fetched once from the (L2-resident) table and kept packed in registers for all frames of the launch.
+template <int N>
+__global__ void __launch_bounds__(K3_BX* K3_BY) k3_warp_u8_kernel(const K3Args a) {
+    const int x = blockIdx.x * K3_BX + threadIdx.x, y = blockIdx.y * K3_BY + threadIdx.y;
+    if (x >= a.dw || y >= a.dh) return;
+    const FixedCoord c = warp_coord(a.wc, x, y);
+    __align__(16) int16_t w[N * N];
+    const int4* wp = reinterpret_cast<const int4*>(a.itab + ((size_t)c.fy * 32 + c.fx) * N * N);
+#pragma unroll
+    for (int i = 0; i < N * N / 8; ++i) reinterpret_cast<int4*>(w)[i] = __ldg(wp + i);
+    const int cv = (int)a.border;
+    const size_t spx = (size_t)a.H * a.W, dpx = (size_t)a.dh * a.dw;
+    const uint8_t* S = (const uint8_t*)a.src;
+    uint8_t* D = (uint8_t*)a.dst + (size_t)y * a.dw + x;
+    for (int f = 0; f < a.n_frames; ++f, S += spx, D += dpx) *D = warp_pixel_u8<N>(S, a.H, a.W, c, w, cv);
+}
+
 // image / tiltFactor in float64 (PerspectiveCorrection.py:394-400: np.asfarray(img) / tf)
 template <typename T>
 __global__ void __launch_bounds__(256) k3_divide_kernel(const T* __restrict__ src, const double* __restrict__ div, double* __restrict__ dst,
@@ -266,10 +284,19 @@ cudaError_t launch_k3(const K3Args& a, int dtype, int interp, int variant, cudaS
     // measured (4096x3000, B200): the staged tiles win for Lanczos4 once a launch carries a few frames (float32 138 vs
     // 160 us/frame, uint16 174 vs 224); a single frame and the 4x4 bicubic window are faster straight through L1
     const bool wanted = variant == 2 || (variant == 0 && interp == WARP_LANCZOS4 && a.n_frames >= 4);
+    if (variant == 2 && dtype == DT_U8) return cudaErrorNotSupported;
     const bool tiled = wanted && ((dtype == DT_U16 && k3_tiled_eligible<uint16_t>(a)) || (dtype == DT_F32 && k3_tiled_eligible<float>(a)));
     if (variant == 2 && !tiled) return cudaErrorNotSupported;
     cudaError_t e;
     switch (dtype) {
+        case DT_U8: {
+            if (!a.itab) return cudaErrorInvalidValue;
+            dim3 block(K3_BX, K3_BY), grid((a.dw + K3_BX - 1) / K3_BX, (a.dh + K3_BY - 1) / K3_BY);
+            if (interp == WARP_LANCZOS4) k3_warp_u8_kernel<8><<<grid, block, 0, st>>>(a);
+            else k3_warp_u8_kernel<4><<<grid, block, 0, st>>>(a);
+            e = cudaGetLastError();
+            break;
+        }
         case DT_U16: e = tiled ? launch_tiled<uint16_t>(a, interp, st) : launch_typed<uint16_t, float>(a, interp, st); break;
         case DT_F32: e = tiled ? launch_tiled<float>(a, interp, st) : launch_typed<float, float>(a, interp, st); break;
         case DT_F64: e = launch_typed<double, double>(a, interp, st); break;

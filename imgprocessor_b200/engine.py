@@ -263,7 +263,7 @@ class Engine(object):
     def warp_perspective(self, src, M, dsize, interpolation='lanczos4', inverse_map=False, border_value=0.0,
                          divide_by=None):
         """K3: cv2.warpPerspective(src, M, dsize=(width, height), flags=INTER_LANCZOS4 | INTER_CUBIC
-        [| WARP_INVERSE_MAP], borderValue) for device frames [n,h,w] or [h,w] of uint16 / float32 / float64
+        [| WARP_INVERSE_MAP], borderValue) for device frames [n,h,w] or [h,w] of uint8 / uint16 / float32 / float64
         (camera/PerspectiveCorrection.py:374-378, 401-405).  divide_by: float64 [h,w] tilt factor applied first
         in float64 (:394-400); the result is then float64.  The frame shape is free (not the engine's)."""
         tt = torch()

@@ -161,9 +161,8 @@ IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* ctx, const void* raw_host, int
  * Replaces cv2.warpPerspective in PerspectiveCorrection.correct (flags=INTER_LANCZOS4,
  * camera/PerspectiveCorrection.py:401-405) and PerspectiveCorrection.uncorrect (INTER_CUBIC |
  * WARP_INVERSE_MAP, :374-378), bit-exact with OpenCV's arithmetic (BORDER_CONSTANT).
- *   src_dev [n][src_h][src_w], dst_dev [n][dst_h][dst_w], both of `dtype` (U16, F32 or F64; uint8's int16
- *   fixed-point weights are not implemented -> IMGCORR_ERR_INVALID); frame sizes are free (<= 32767 per side),
- *   the context only supplies the device.
+ *   src_dev [n][src_h][src_w], dst_dev [n][dst_h][dst_w], both of `dtype` (U8 with OpenCV's int16 fixed-point
+ *   weights, U16, F32 or F64); frame sizes are free (<= 32767 per side), the context only supplies the device.
  *   M             3x3 row-major homography src -> dst (the matrix cv2.warpPerspective takes); inverted here
  *                 with cv::invert's cofactor formula unless inverse_map != 0
  *   interpolation IMGCORR_INTER_LANCZOS4 or IMGCORR_INTER_CUBIC (values of the cv2 flags) */

@@ -25,7 +25,8 @@ OpenCV is un-vendored; the model restates its published algorithm (imgwarp.cpp):
     window entirely outside: the border value.
 Validated bit for bit against OpenCV 4.13.0 in tests/test_oracle_models.py and
 against the reference's own PerspectiveCorrection outputs (tests/golden).
-uint8 images (OpenCV's int16 fixed-point weights) are not modelled.
+uint8 images use OpenCV's fixed-point branch: int16 weights = saturate_cast<short>(wy * wx * 2**15) with the sum of each
+phase pair's table forced to 2**15 on one of the four central taps (initInterTab2D), int32 accumulation, rounding shift.
 """
 import numpy as np
 
@@ -94,6 +95,56 @@ def cubic_table():
     return tab
 
 
+def fixed_point_table(tab):
+    """initInterTab2D, fixed-point branch: int16 weights [32][32][n*n] (phase fy, phase fx, tap row-major)."""
+    n = tab.shape[1]
+    out = np.zeros((INTER_TAB_SIZE, INTER_TAB_SIZE, n * n), np.int16)
+    k2 = n // 2
+    for i in range(INTER_TAB_SIZE):
+        for j in range(INTER_TAB_SIZE):
+            v = (tab[i][:, None] * tab[j][None, :]).astype(np.float32)
+            it = np.clip(np.rint(v * np.float32(32768)), -32768, 32767).astype(np.int64).ravel()
+            diff = int(it.sum()) - 32768
+            if diff != 0:
+                Mk = mk = (k2, k2)
+                for a in range(k2, k2 + 2):
+                    for b in range(k2, k2 + 2):
+                        if it[a * n + b] < it[mk[0] * n + mk[1]]:
+                            mk = (a, b)
+                        elif it[a * n + b] > it[Mk[0] * n + Mk[1]]:
+                            Mk = (a, b)
+                k = Mk if diff < 0 else mk
+                it[k[0] * n + k[1]] -= diff
+            out[i, j] = it
+    return out
+
+
+def _warp_u8(src, tab, n, off, coords, border_value):
+    it = fixed_point_table(tab).astype(np.int64)
+    ix, iy, fx, fy = coords
+    H, W = src.shape
+    sx, sy = ix - off, iy - off
+    fast = (sx >= 0) & (sx < max(W - (n - 1), 0)) & (sy >= 0) & (sy < max(H - (n - 1), 0))
+    outside = (sx >= W) | (sx + n <= 0) | (sy >= H) | (sy + n <= 0)
+    w = it[fy, fx]
+    cv = int(np.clip(np.rint(border_value), 0, 255))
+    total = np.zeros(ix.shape, np.int64)
+    edge = np.full(ix.shape, cv * 32768, np.int64)
+    s64 = src.astype(np.int64)
+    for r in range(n):
+        yy = sy + r
+        yin = (yy >= 0) & (yy < H)
+        yc = np.clip(yy, 0, H - 1)
+        for c in range(n):
+            xx = sx + c
+            xin = (xx >= 0) & (xx < W)
+            v = s64[yc, np.clip(xx, 0, W - 1)]
+            total += v * w[..., r * n + c]
+            edge += np.where(yin & xin, (v - cv) * w[..., r * n + c], 0)
+    res = np.where(fast, total, np.where(outside, cv * 32768, edge))
+    return np.clip((res + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
 def warp_coords(M, dsize, inverse_map=False):
     """Fixed-point source coordinates of every output pixel: (ix, iy, fx, fy), int64 [h][w]."""
     w, h = int(dsize[0]), int(dsize[1])
@@ -129,13 +180,13 @@ def warp_coords(M, dsize, inverse_map=False):
 def warp_perspective_model(src, M, dsize, interpolation='lanczos4', inverse_map=False, border_value=0.0,
                            divide_by=None):
     """cv2.warpPerspective(src, M, dsize, flags=INTER_LANCZOS4 | INTER_CUBIC [| WARP_INVERSE_MAP],
-    borderMode=BORDER_CONSTANT, borderValue) for a 2-D uint16 / float32 / float64 image.
+    borderMode=BORDER_CONSTANT, borderValue) for a 2-D uint8 / uint16 / float32 / float64 image.
     divide_by: the tilt-factor division of PerspectiveCorrection.correct (:394-400) applied first,
     in float64 (the image becomes float64, as np.asfarray does there)."""
     src = np.asarray(src)
     if divide_by is not None:
         src = np.asarray(src, np.float64) / np.asarray(divide_by, np.float64)
-    if src.dtype not in (np.uint16, np.float32, np.float64):
+    if src.dtype not in (np.uint8, np.uint16, np.float32, np.float64):
         raise TypeError('unmodelled dtype %s' % src.dtype)
     if interpolation == 'lanczos4':
         tab, n, off = lanczos4_table(), 8, 3
@@ -144,6 +195,8 @@ def warp_perspective_model(src, M, dsize, interpolation='lanczos4', inverse_map=
     else:
         raise ValueError(interpolation)
     ix, iy, fx, fy = warp_coords(M, dsize, inverse_map)
+    if src.dtype == np.uint8:
+        return _warp_u8(src, tab, n, off, (ix, iy, fx, fy), border_value)
     H, W = src.shape
     wt = np.float64 if src.dtype == np.float64 else np.float32
     sx, sy = ix - off, iy - off

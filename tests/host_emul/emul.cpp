@@ -160,7 +160,7 @@ static void warp_typed(const T* src, T* dst, int H, int W, int dh, int dw, const
         }
 }
 
-// dtype: 1 u16, 2 f32, 3 f64;  interp: 2 cubic, 4 lanczos4
+// dtype: 0 u8, 1 u16, 2 f32, 3 f64;  interp: 2 cubic, 4 lanczos4
 extern "C" __attribute__((visibility("default")))
 int emul_warp(const void* src, int dtype, void* dst, int H, int W, int dh, int dw, const double* M, int interp, int inverse,
               double border) {
@@ -170,6 +170,20 @@ int emul_warp(const void* src, int dtype, void* dst, int H, int W, int dh, int d
     border = border_for_dtype(0, dtype == 1, border);
 #define GO(T, AT) { if (interp == WARP_LANCZOS4) warp_typed<T, AT, 8>((const T*)src, (T*)dst, H, W, dh, dw, wc, tab.data(), border); \
                     else warp_typed<T, AT, 4>((const T*)src, (T*)dst, H, W, dh, dw, wc, tab.data(), border); }
+    if (dtype == 0) {
+        const int n = interp == WARP_LANCZOS4 ? 8 : 4;
+        std::vector<int16_t> it((size_t)32 * 32 * n * n);
+        warp_fixed_table(tab.data(), n, it.data());
+        border = border_for_dtype(1, 0, border);
+        for (int y = 0; y < dh; ++y)
+            for (int x = 0; x < dw; ++x) {
+                const FixedCoord c = warp_coord(wc, x, y);
+                const int16_t* w = it.data() + ((size_t)c.fy * 32 + c.fx) * n * n;
+                ((uint8_t*)dst)[(size_t)y * dw + x] = n == 8 ? warp_pixel_u8<8>((const uint8_t*)src, H, W, c, w, (int)border)
+                                                             : warp_pixel_u8<4>((const uint8_t*)src, H, W, c, w, (int)border);
+            }
+        return 0;
+    }
     if (dtype == 1) GO(uint16_t, float) else if (dtype == 2) GO(float, float) else if (dtype == 3) GO(double, double) else return -1;
 #undef GO
     return 0;

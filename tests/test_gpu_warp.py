@@ -60,6 +60,8 @@ class _Eng(object):
 
 def _img(dt, shape, seed=0):
     a = np.random.default_rng(seed).random(shape)
+    if dt == np.uint8:
+        return (a * 255).astype(np.uint8)
     return (a * 65535).astype(np.uint16) if dt == np.uint16 else a.astype(dt)
 
 
@@ -67,7 +69,7 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-@pytest.mark.parametrize('dt', [np.float32, np.float64, np.uint16])
+@pytest.mark.parametrize('dt', [np.float32, np.float64, np.uint16, np.uint8])
 @pytest.mark.parametrize('interp', ['lanczos4', 'cubic'])
 def test_k3_bit_exact(eng, dt, interp):
     img = _img(dt, (90, 130))
@@ -111,11 +113,13 @@ def test_k3_degenerate_and_special_values(eng):
 
 
 def test_k3_batch_and_division(eng):
-    frames = np.stack([_img(np.uint16, (120, 160), s) for s in range(5)])
     M = MATS[0]
-    got = eng.warp_perspective(_dev(frames), M, (140, 100)).cpu().numpy()
-    for i in range(5):
-        assert np.array_equal(got[i], cv2.warpPerspective(frames[i], M, (140, 100), flags=cv2.INTER_LANCZOS4))
+    for dt in (np.uint16, np.uint8):
+        frames = np.stack([_img(dt, (120, 160), s) for s in range(5)])
+        got = eng.warp_perspective(_dev(frames), M, (140, 100)).cpu().numpy()
+        for i in range(5):
+            assert np.array_equal(got[i], cv2.warpPerspective(frames[i], M, (140, 100), flags=cv2.INTER_LANCZOS4))
+    frames = np.stack([_img(np.uint16, (120, 160), s) for s in range(5)])
     tf = 0.5 + np.random.default_rng(5).random((120, 160))
     got = eng.warp_perspective(_dev(frames), M, (140, 100), divide_by=torch.from_numpy(tf)).cpu().numpy()
     assert got.dtype == np.float64
@@ -140,8 +144,8 @@ def test_k3_full_frame(eng):
 
 def test_k3_rejects(eng):
     from imgprocessor_b200 import _lib
-    with pytest.raises(_lib.ImgcorrError):
-        eng.warp_perspective(_dev(np.zeros((8, 8), np.uint8)), np.eye(3), (8, 8))
+    with pytest.raises(TypeError):
+        eng.warp_perspective(_dev(np.zeros((8, 8), np.int32)), np.eye(3), (8, 8))
     param, eng = eng.param, eng.e
     eng.set_option(_lib.OPT_K3_VARIANT, 2)
     try:
@@ -149,6 +153,8 @@ def test_k3_rejects(eng):
             eng.warp_perspective(_dev(np.zeros((8, 130), np.float32)), np.eye(3), (8, 8))
         with pytest.raises(_lib.ImgcorrError):
             eng.warp_perspective(_dev(np.zeros((8, 128), np.float64)), np.eye(3), (8, 8))
+        with pytest.raises(_lib.ImgcorrError):
+            eng.warp_perspective(_dev(np.zeros((8, 128), np.uint8)), np.eye(3), (8, 8))
         out = eng.warp_perspective(_dev(_img(np.float32, (64, 128))), MATS[1], (128, 64)).cpu().numpy()
         assert np.array_equal(out, cv2.warpPerspective(_img(np.float32, (64, 128)), MATS[1], (128, 64), flags=cv2.INTER_LANCZOS4))
     finally:

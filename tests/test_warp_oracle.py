@@ -19,6 +19,8 @@ QUADS = [np.array([[0.5, 0.1, -20], [0.05, 0.7, -30], [1e-4, -2e-4, 1.0]]),
 def _img(dt, shape=(90, 130), seed=0):
     rng = np.random.default_rng(seed)
     a = rng.random(shape)
+    if dt == np.uint8:
+        return (a * 255).astype(np.uint8)
     return (a * 65535).astype(np.uint16) if dt == np.uint16 else a.astype(dt)
 
 
@@ -43,7 +45,7 @@ def test_tables_and_invert_match_opencv():
     assert np.array_equal(W.invert3x3_cv(np.zeros((3, 3))), np.zeros((3, 3)))
 
 
-@pytest.mark.parametrize('dt', [np.float32, np.float64, np.uint16])
+@pytest.mark.parametrize('dt', [np.float32, np.float64, np.uint16, np.uint8])
 @pytest.mark.parametrize('interp', ['lanczos4', 'cubic'])
 def test_model_and_emul_match_opencv(dt, interp):
     img = _img(dt)
