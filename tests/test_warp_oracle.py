@@ -138,3 +138,53 @@ def test_sort_corners_and_quad_homography():
     assert np.array_equal(sortCorners(g['quad']), g['quad_sorted'])
     K = genericCameraMatrix((120, 160))
     assert K.dtype == np.float32 and K[0, 2] == 80 and K[1, 2] == 60
+
+
+def test_random_homographies_emul_vs_opencv():
+    """seeded sweep: random quads -> homographies (zoom, rotation, keystone), random sizes / dtypes / borders"""
+    rng = np.random.default_rng(2024)
+    for t in range(40):
+        H, Wd = int(rng.integers(9, 70)), int(rng.integers(9, 90))
+        dt = [np.uint8, np.uint16, np.float32, np.float64][t % 4]
+        img = _img(dt, (H, Wd), seed=t)
+        dw, dh = int(rng.integers(1, 100)), int(rng.integers(1, 80))
+        quad = np.float32([[0, 0], [Wd, 0], [Wd, H], [0, H]]) + rng.normal(0, 0.15 * min(H, Wd), (4, 2)).astype(np.float32)
+        dst = np.float32([[0, 0], [dw, 0], [dw, dh], [0, dh]])
+        try:
+            M = cv2.getPerspectiveTransform(quad, dst)
+        except cv2.error:
+            continue
+        interp, flag = (('lanczos4', cv2.INTER_LANCZOS4), ('cubic', cv2.INTER_CUBIC))[t % 2]
+        inv = bool((t // 2) % 2)
+        border = float(rng.integers(0, 300))
+        ref = cv2.warpPerspective(img, M, (dw, dh), flags=flag | (cv2.WARP_INVERSE_MAP if inv else 0), borderValue=border)
+        assert np.array_equal(emul.warp(img, M, (dw, dh), interp, inv, border), ref.reshape(dh, dw), equal_nan=True), t
+
+
+def test_perspective_correction_host_logic():
+    """the mirror's host side without a GPU: argument conventions and the loud refusals"""
+    from imgprocessor_b200.camera.PerspectiveCorrection import PerspectiveCorrection, sortCorners
+    pc = PerspectiveCorrection((120, 160), new_size=(96, 136), border=4)
+    g = load_golden('perspective')
+    pc.setReference(g['quad'])
+    assert np.array_equal(pc.quad, g['quad_sorted'])
+    assert np.array_equal(pc.homography, g['quad_homography'])          # cv2.getPerspectiveTransform on the sorted quad
+    assert pc.obj_points.shape == (4, 3) and pc.obj_points.dtype == np.float32
+    area = pc.areaRatio
+    assert area > 0.9 and area < 1.5
+    pts = pc.correctPoints(np.float32(g['quad_sorted']))
+    assert np.allclose(pts[0], [[4, 4], [132, 4], [132, 92], [4, 92]], atol=1e-3)   # the quad lands on the bordered target
+    with pytest.raises(NotImplementedError):
+        pc.setReference(np.zeros((50, 60)))                               # reference IMAGE: PatternRecognition path
+    with pytest.raises(ValueError):
+        sortCorners([[0, 0], [10, 0], [3, 2], [0, 10]])                   # concave
+    with pytest.raises(NotImplementedError):
+        PerspectiveCorrection((120, 160)).setReference(g['quad'])         # new_size not given
+    pc2 = PerspectiveCorrection((120, 160), new_size=(96, 136), do_correctIntensity=True)
+    with pytest.raises(NotImplementedError):
+        pc2.tiltFactor()
+    pc2.setTiltFactor(np.ones((120, 160)))
+    assert pc2.tiltFactor().dtype == np.float64
+    with pytest.raises(NotImplementedError):
+        PerspectiveCorrection._cv2_opts({'borderMode': 1})
+    assert PerspectiveCorrection._cv2_opts({'borderValue': (3.0, 0, 0, 0)}) == 3.0
