@@ -206,6 +206,14 @@ constexpr int KT_NBUF = KT_NBUF_V;                       // frames of a launch i
 constexpr int KT_SMEM = KT_NBUF * KT_BOX_BYTES + 128;
 
 
+// predicated global store: a plain `if (flag) *p = v` lets ptxas wrap the whole gather of that pixel in a branch
+__device__ __forceinline__ void st_if(float* p, float v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(flag) : "memory");
+}
+__device__ __forceinline__ void st_if(double* p, double v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(flag) : "memory");
+}
+
 template <typename DstT, int MODE>
 __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, K2Args a) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -287,7 +295,10 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
     if (fits) {
         int so[KT_PX];
 #pragma unroll
-        for (int j = 0; j < KT_PX; ++j) so[j] = (fast & (1u << j)) ? (ciy[j] - by) * KT_BW + (cix[j] - bx) : 0;
+        for (int j = 0; j < KT_PX; ++j) {
+            so[j] = (fast & (1u << j)) ? (ciy[j] - by) * KT_BW + (cix[j] - bx) : 0;
+            asm volatile("" : "+r"(so[j]));            // keep the offset: ptxas otherwise recomputes it from cix / ciy every frame
+        }
         auto issue = [&](int f) {
             uint64_t* bar = &full[f % KT_NBUF];
             mbar_expect_tx(bar, KT_BOX_BYTES);
@@ -302,7 +313,7 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
             for (int j = 0; j < KT_PX; ++j) {
                 const float* p = box + so[j];
                 const float r = blend_f32(p[0], p[1], p[KT_BW], p[KT_BW + 1], wt[j].w00, wt[j].w01, wt[j].w10, wt[j].w11);
-                if (fast & (1u << j)) dst[j * dstep] = (DstT)r;
+                st_if(dst + j * dstep, (DstT)r, fast & (1u << j));      // predicated store, no branch around the gather
             }
             dst += dst_stride;
             __syncthreads();                           // everyone is done with this buffer
