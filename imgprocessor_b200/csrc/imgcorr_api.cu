@@ -177,6 +177,7 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
             c->k1_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
+            if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k2 variant %d", value);
             c->k2_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_CHAIN_OVERLAP:
