@@ -46,6 +46,16 @@ def _getFromDate(entries, date):
     return entries[0] if i == -1 else entries[i]
 
 
+def _map_token(kind, arr):
+    """identity of a calibration map for the engine's upload cache: the array object plus a fingerprint of ~4000 strided
+    samples, so that an array modified in place between two calls is uploaded again (the reference reads it every call)"""
+    if not isinstance(arr, np.ndarray):
+        return None
+    flat = arr.reshape(-1)
+    step = max(1, flat.size // 4096)
+    return (kind, id(arr), arr.shape, arr.dtype.str, hash(flat[::step].tobytes()))
+
+
 class _BoundedNLF(object):
     """NoiseLevelFunction.boundedFunction(x, minY, ax, ay) (camera/NoiseLevelFunction.py:94-107) with its parameters
     kept, so that kernel K4 can evaluate it per pixel; calling it evaluates the same expression with numpy."""
@@ -323,7 +333,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
             bg = entry[2]
         self.temp['bg'] = bg
         np.broadcast_to(np.asarray(bg), shape)           # same failure as `image -= bg` for a bad shape
-        return dict(dark=bg, ascent=None, exposure=0.0, token=('dark', id(bg)) if isinstance(bg, np.ndarray) else None)
+        return dict(dark=bg, ascent=None, exposure=0.0, token=_map_token('dark', bg))
 
     def _configure_engine(self, eng, shape, bgImages, exposure_time, light_spectrum, date, use_dark=True):
         """upload whatever calibration applies; returns (flags, lens-or-None)"""
@@ -345,7 +355,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
                 print('... remove vignetting and sensitivity')
                 flat = f[2]
                 np.broadcast_to(np.asarray(flat), shape)
-                eng.set_flat(flat, token=('flat', id(flat)) if isinstance(flat, np.ndarray) else None)
+                eng.set_flat(flat, token=_map_token('flat', flat))
                 flags |= _lib.DO_FLAT
                 self._last_flat = flat
         except _lib.ImgcorrError:

@@ -589,6 +589,20 @@ def test_correct_batch_device_and_host(ip):
     assert r is pin_out and np.array_equal(pin_out.astype(np.float64), single[:, y:y + h, x:x + w])
 
 
+def test_calibration_modified_in_place_is_uploaded_again(ip):
+    """the reference reads its calibration arrays on every call; the engine's upload cache must notice an in-place edit"""
+    g = dict(load_golden('correct_u16_keep1'))
+    g['dark'] = g['dark'].copy()
+    cal = _cal(ip, g, lens=False)
+    raw = g['raw']
+    out1, _ = _quiet(cal.correct, raw, threshold=0.1)
+    g['dark'] += 50.0                                                # same array object, new content
+    out2, _ = _quiet(cal.correct, raw, threshold=0.1)
+    want = refpath.correct(raw, g['dark'], g['flat'], None, 0.1)
+    assert not np.array_equal(out1, out2)
+    assert np.abs(out2 - want).max() <= 1e-5 * 65535
+
+
 def test_chain_overlap_mode_is_identical(ip):
     """IMGCORR_OPT_CHAIN_OVERLAP: K1 of group g+1 on the internal high-priority stream while K2 of group g runs — same
     output for every group size (buffer hand-off by events), with and without profiling brackets"""

@@ -93,3 +93,15 @@ def test_parse_cpulist_and_numa_binding(tmp_path, monkeypatch):
     before = os.sched_getaffinity(0)
     info = sharding.bind_host_to_gpu(0, sysfs=str(tmp_path))
     assert info['bound'] is False and os.sched_getaffinity(0) == before
+
+
+def test_calibration_upload_token_sees_in_place_changes():
+    from imgprocessor_b200.camera.CameraCalibration import _map_token
+    a = np.random.default_rng(0).random((300, 400)).astype(np.float32)
+    t0 = _map_token('dark', a)
+    assert t0 == _map_token('dark', a) and t0 != _map_token('flat', a)
+    a *= 2                                       # in place: same object, new content
+    assert _map_token('dark', a) != t0
+    assert _map_token('dark', 3.0) is None
+    b = a[::2]                                   # non-contiguous views work too
+    assert _map_token('dark', b) == _map_token('dark', b)
