@@ -343,6 +343,16 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=3)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.gpus > 1 and 'WORLD_SIZE' not in os.environ and args.impl == 'ours':
+        # started as plain `python bench.py --gpus N`: relaunch under torchrun, one rank per GPU (the driver does this itself)
+        import socket
+        with socket.socket() as sk:
+            sk.bind(('127.0.0.1', 0))
+            port = sk.getsockname()[1]
+        os.execv(sys.executable, [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(args.gpus),
+                                  '--master-addr', '127.0.0.1', '--master-port', str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    if 'WORLD_SIZE' in os.environ and int(os.environ['WORLD_SIZE']) != args.gpus and args.impl == 'ours':
+        raise SystemExit('bench.py: --gpus %d but WORLD_SIZE=%s' % (args.gpus, os.environ['WORLD_SIZE']))
     args.k1_traffic = None
     try:        # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch from the committed ncu --set full capture
         with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
