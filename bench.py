@@ -320,7 +320,11 @@ def run_ours(args):
                          'k2': {'achieved': k2_achieved, 'frac': k2_achieved / peak, 'us_per_frame': k2_us,
                                 'algorithmic_bytes_per_px': K2_BYTES_PER_PX},
                          'chain_frac': (K1_BYTES_PER_PX + K2_BYTES_PER_PX) * H * W / ((k1_us + k2_us) * 1e-6) / 1e9 / peak
-                                       if k1_us + k2_us > 0 else 0.0},
+                                       if k1_us + k2_us > 0 else 0.0,
+                         'chain_overlap': bool(args.overlap),
+                         'timing_note': 'K1 / K2 durations are event-bracketed launches inside the timed region; with chain_overlap '
+                                        'the bracketed frame groups run unoverlapped (kernel alone), the others overlap K1 of group '
+                                        'g+1 with K2 of group g, so ms_per_step can be below frames * (K1 + K2)'},
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_single()

@@ -74,7 +74,7 @@ enum {
     IMGCORR_OPT_RAW_FRAME_GAP = 8,  /* bytes between the end of one raw frame and the start of the next: reader/elbin.py:23-32
                                        (a 20-byte header precedes every frame).  Not available for the *_host entry point. */
     IMGCORR_OPT_CHAIN_OVERLAP = 10, /* imgcorr_correct_batch: run K1 of the next frame group on an internal high-priority stream while K2
-                                       of the current group runs on the caller's stream (default 0 = one stream) */
+                                       of the current group runs on the caller's stream (default 0 = everything on the caller's stream) */
     IMGCORR_OPT_K3_VARIANT = 9      /* 0 auto, 1 gathers through L1/L2, 2 shared-memory staged tiles (uint16 / float32 sources; fails if not eligible) */
 };
 
