@@ -7,7 +7,9 @@
 //     out-of-frame lanes read the mirrored column = scipy 'reflect').  Per row: pointwise value in float64 registers,
 //     the four horizontal neighbours by warp shuffle, a 9-comparator sort of the horizontal quintuple — shared by the
 //     five windows that row takes part in —, and the generated 57-comparator selection network (median25_net.inc)
-//     over this quintuple and the four previous rows' quintuples held in registers.
+//     over this quintuple and the four previous rows' quintuples held in registers.  The window holds order-preserving
+//     integer keys: a compare-exchange is one VIMNMX plus max = a + b - min as two IMADs (FMA pipe), because two
+//     FMNMX per exchange saturate the half-rate ALU pipe.
 //   * vertical 'reflect': rows -1, -2 are rows 0, 1 (the window is primed with Q1, Q0, Q0, Q1), rows H, H+1 are rows
 //     H-1, H-2 (two more emits after the last row).
 //
@@ -17,6 +19,18 @@
 
 namespace imgcorr {
 
+#if !defined(K5_INTKEYS) || K5_INTKEYS
+__constant__ int k5_one = 1, k5_minus_one = -1;   // run-time values for ptxas: keeps the two IMADs from folding into IADD3
+template <> __device__ __forceinline__ void cswap<OrdKey>(OrdKey& a, OrdKey& b) {
+    const int lo = a.k < b.k ? a.k : b.k;
+    int hi;
+    asm("{\n\t.reg .s32 t;\n\tmad.lo.s32 t, %1, %4, %2;\n\tmad.lo.s32 %0, %3, %5, t;\n\t}"
+        : "=r"(hi) : "r"(a.k), "r"(b.k), "r"(lo), "r"(k5_one), "r"(k5_minus_one));
+    b.k = hi;
+    a.k = lo;
+}
+#endif
+
 namespace {
 
 constexpr int K5_HW = 2;                    // halo width
@@ -24,7 +38,7 @@ constexpr int K5_CW = 4;                    // consumer warps per CTA
 constexpr int K5_SW = 32 - 2 * K5_HW;       // 28 output columns per consumer warp
 constexpr int K5_TW = K5_CW * K5_SW;        // 112 output columns per strip
 #ifndef K5_MINB_V
-#define K5_MINB_V 4
+#define K5_MINB_V 3
 #endif
 constexpr int K5_R = 8;                     // rows per pipeline stage
 constexpr int K5_NSTAGE = 4;
@@ -60,7 +74,23 @@ __device__ __noinline__ bool exact5(float x, float b, double thr, int cond) {
     return predicate_exact((double)x, (double)b, pc);
 }
 
-struct Q5 { float v[5]; };                  // sorted horizontal quintuple of one row
+#ifndef K5_INTKEYS
+#define K5_INTKEYS 1
+#endif
+#if K5_INTKEYS
+typedef OrdKey K5T;                         // the window holds order-preserving integer keys (see imgcorr_core.cuh)
+__device__ __forceinline__ K5T k5_in(float x) { return to_key(x); }
+__device__ __forceinline__ float k5_out(K5T q) { return from_key(q); }
+__device__ __forceinline__ K5T k5_shfl_up(K5T c, int d) { K5T r; r.k = __shfl_up_sync(0xffffffffu, c.k, d); return r; }
+__device__ __forceinline__ K5T k5_shfl_down(K5T c, int d) { K5T r; r.k = __shfl_down_sync(0xffffffffu, c.k, d); return r; }
+#else
+typedef float K5T;
+__device__ __forceinline__ K5T k5_in(float x) { return x; }
+__device__ __forceinline__ float k5_out(K5T q) { return q; }
+__device__ __forceinline__ K5T k5_shfl_up(K5T c, int d) { return __shfl_up_sync(0xffffffffu, c, d); }
+__device__ __forceinline__ K5T k5_shfl_down(K5T c, int d) { return __shfl_down_sync(0xffffffffu, c, d); }
+#endif
+struct Q5 { K5T v[5]; };                    // sorted horizontal quintuple of one row
 
 struct Unit5 {
     int frame, tx0, ys, ye, yl0, n_in, nchunk;
@@ -170,19 +200,20 @@ k1_stream5_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
         };
         auto quint = [&](float x) -> Q5 {
             Q5 q;
-            q.v[0] = __shfl_up_sync(0xffffffffu, x, 2);
-            q.v[1] = __shfl_up_sync(0xffffffffu, x, 1);
-            q.v[2] = x;
-            q.v[3] = __shfl_down_sync(0xffffffffu, x, 1);
-            q.v[4] = __shfl_down_sync(0xffffffffu, x, 2);
+            const K5T c = k5_in(x);                      // one conversion per pixel; the neighbours arrive as keys
+            q.v[0] = k5_shfl_up(c, 2);
+            q.v[1] = k5_shfl_up(c, 1);
+            q.v[2] = c;
+            q.v[3] = k5_shfl_down(c, 1);
+            q.v[4] = k5_shfl_down(c, 2);
             sort5(q.v);
             return q;
         };
         auto median = [&](const Q5& q) -> float {
-            float v[25];
+            K5T v[25];
 #pragma unroll
             for (int k = 0; k < 5; ++k) { v[k] = w0.v[k]; v[5 + k] = w1.v[k]; v[10 + k] = w2.v[k]; v[15 + k] = w3.v[k]; v[20 + k] = q.v[k]; }
-            return median25_sorted_rows(v);
+            return k5_out(median25_sorted_rows(v));
         };
         auto emit = [&](const Q5& q, bool on) {
             const float med = median(q);

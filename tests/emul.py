@@ -102,3 +102,11 @@ def ste(frames, nlf, n_std=4.0, want_mask=False):
     mask = np.zeros((H, W), np.uint8) if want_mask else None
     lib().emul_ste(_p(frames), n, H, W, _p(np.ascontiguousarray(nlf, np.float64)), ctypes.c_double(n_std), _p(avg), _p(mask))
     return (avg, mask.astype(bool)) if want_mask else avg
+
+
+def keys(x):
+    x = np.ascontiguousarray(x, np.float32)
+    k = np.empty(x.shape, np.int32)
+    back = np.empty(x.shape, np.float32)
+    lib().emul_keys(_p(x), x.size, _p(k), _p(back))
+    return k, back

@@ -226,3 +226,9 @@ void emul_ste(const double* frames, int n, int H, int W, const double* nlf, doub
             }
     }
 }
+
+// order-preserving integer keys used by the 5x5 streaming kernel (imgcorr_core.cuh: to_key / from_key)
+extern "C" __attribute__((visibility("default")))
+void emul_keys(const float* x, int n, int* keys, float* back) {
+    for (int i = 0; i < n; ++i) { OrdKey k = to_key(x[i]); keys[i] = k.k; back[i] = from_key(k); }
+}

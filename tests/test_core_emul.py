@@ -169,3 +169,18 @@ def test_full_chain_vs_reference_golden():
     assert np.abs(out[ok] - g['out'][ok]).max() / 65535.0 < 1e-5
     want, _ = models.correct_chain_f32(g['raw'], g['dark'], g['flat'], 0.1, 3, mapxy=(mx, my))
     assert np.array_equal(out, want)
+
+
+def test_order_preserving_keys():
+    """the 5x5 streaming kernel sorts integer keys instead of floats: the mapping must be a bijection that preserves
+    the order PTX min / max use (-0.0 below +0.0), over denormals, infinities and the whole finite range"""
+    rng = np.random.default_rng(12)
+    x = np.concatenate([rng.normal(0, 1e3, 5000), rng.normal(0, 1e-40, 500), [0.0, -0.0, np.inf, -np.inf, 3.4e38, -3.4e38,
+                        1e-45, -1e-45, 1.0, -1.0]]).astype(np.float32)
+    k, back = emul.keys(x)
+    assert np.array_equal(back.view(np.uint32), x.view(np.uint32))              # exact round trip, sign of zero included
+    order = np.argsort(k, kind='stable')
+    xs = x[order]
+    assert np.all(xs[:-1] <= xs[1:])                                            # same order as the floats
+    kz, _ = emul.keys(np.array([-0.0, 0.0], np.float32))
+    assert kz[0] < kz[1]
