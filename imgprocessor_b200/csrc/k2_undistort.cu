@@ -193,8 +193,14 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
 //     box origin = (min ix rounded down to 4 columns — TMA's 16-byte rule —, min iy).  If the window does not fit the
 //     fixed 80x32 box (very strong distortion) the tile falls back to global gathers: correct for any map;
 //   * rim pixels (window touching the frame border) are redone from global memory with per-neighbour border handling.
-constexpr int KT_TW = 64, KT_TH = 16, KT_THREADS = 256, KT_PX = 4;
-constexpr int KT_BW = 80, KT_BH = 32;
+#ifndef KT_TW_V
+#define KT_TW_V 64
+#define KT_TH_V 16
+#define KT_BW_V 80
+#define KT_BH_V 32
+#endif
+constexpr int KT_TW = KT_TW_V, KT_TH = KT_TH_V, KT_THREADS = 256, KT_PX = KT_TW * KT_TH / KT_THREADS;
+constexpr int KT_BW = KT_BW_V, KT_BH = KT_BH_V;
 constexpr int KT_BOX_BYTES = KT_BW * KT_BH * 4;          // 10240
 #ifndef KT_NBUF_V
 #define KT_NBUF_V 4
