@@ -92,7 +92,9 @@ __device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int 
 
 // CFG >= 0 bakes the per-launch switches into the instruction stream (the kernel is issue bound: every
 // per-row flag test costs); CFG < 0 reads them from the arguments.
-enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32, KS_NZ = 64, KS_SWAP = 128 };
+enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, KS_LT = 32, KS_NZ = 64, KS_SWAP = 128, KS_NOMED = 256 };
+// KS_NOMED: ksize 0 (threshold <= 0, CameraCalibration.py:556-557 skips the artefact step): the pointwise value itself is
+// stored, through the same pipeline (one row late, like the median's centre pixel)
 // KS_SWAP: big-endian uint16 samples (reader/RAW.py default) — one PRMT per pixel after the shared-memory load
 // KS_NZ: a.flat is the zero-free copy (zeros replaced by 1.0) -> unconditional division
 // KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
@@ -111,6 +113,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     const bool has_mask = CFG >= 0 ? (CFG & KS_MASK) != 0 : a.mask != nullptr;
     const bool check = CFG >= 0 ? (CFG & KS_CHECK) != 0 : true;
     const bool swap = CFG >= 0 ? (CFG & KS_SWAP) != 0 : a.raw_swap != 0;
+    const bool nomed = CFG >= 0 ? (CFG & KS_NOMED) != 0 : a.ksize == 0;
     const int flags = CFG >= 0 ? ((CFG & KS_DARK ? FLAG_DARK : 0) | (CFG & KS_FLAT ? FLAG_FLAT : 0) | (CFG & KS_N2N ? FLAG_NAN_TO_NUM : 0))
                                : a.pw.flags;
     const int H = a.H, W = a.W;
@@ -184,6 +187,10 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
             return x;
         };
         auto emit = [&](const Sorted3<float>& t2, bool on) {
+            if (nomed) {
+                if (on) *outp = ks_out<OutT>(c1);
+                return;
+            }
             const float med = median9(s0, s1, t2);
             bool rep;
             const bool sure = predicate_certain(c1, med, pred, rep);
@@ -240,6 +247,12 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 #pragma unroll
                 for (int j = 0; j < KS_R; ++j) {
                     const float x = pixel(base, j);
+                    if (nomed) {
+                        *op = ks_out<OutT>(c1);
+                        op += ostride;
+                        c1 = x;
+                        continue;
+                    }
                     const float l = __shfl_up_sync(0xffffffffu, x, 1);
                     const float r = __shfl_down_sync(0xffffffffu, x, 1);
                     const Sorted3<float> t2 = sort3(l, x, r);
@@ -276,7 +289,8 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
 
 // ------------------------------------------------------------------------------------------ host
 bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
-    if (a.ksize != 3) return false;
+    if (a.ksize != 3 && a.ksize != 0) return false;
+    if (a.ksize == 0 && a.H < 4) return false;
     if (raw_dtype != DT_U8 && raw_dtype != DT_U16 && raw_dtype != DT_F32) return false;
     if (out_dtype != DT_F32 && !(raw_dtype == DT_U16 && out_dtype == DT_U16) && !(raw_dtype == DT_U8 && out_dtype == DT_U8)) return false;
     if (a.pw.flags & FLAG_DARK_LINEAR) return false;
@@ -297,13 +311,19 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     // pick the instantiation: the hot configurations are fully specialised, the rest read their flags at run time
     const bool check = !a.maps_finite || sizeof(RawT) == 4;
     const int f = a.pw.flags;
-    const bool chain = a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
+    const bool chain = a.ksize == 3 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
                        a.pred.cond == COND_GT;
-    const bool plain = !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
+    const bool plain = a.ksize == 3 && !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
     void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
     int slot;
-    if (chain) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
-    if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
+    // threshold <= 0: dark + flat only (nan_to_num is not applied then, CameraCalibration.py:556-561)
+    const bool pw_only = a.ksize == 0 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && !a.raw_swap && !check;
+    if (chain || pw_only) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
+    if (pw_only) {
+        kern = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_NOMED>
+                                                       : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_NOMED>;
+        slot = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? 7 : 8;
+    } else if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
         kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP>
                              : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP>;
         slot = a.no_overflow ? 5 : 6;
@@ -320,7 +340,7 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
         return cudaErrorInvalidValue;
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
-    static int per_sm[7] = {0, 0, 0, 0, 0, 0, 0};
+    static int per_sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (!per_sm[slot]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
         if (e != cudaSuccess) return e;

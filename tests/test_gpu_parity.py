@@ -235,6 +235,30 @@ def test_k1_stream5_batch_and_guard_band(ip):
     e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
 
 
+@pytest.mark.parametrize('seg_rows', [0, 4, 7, 16, 33])
+@pytest.mark.parametrize('dtype', [np.uint16, np.float32, np.uint8])
+def test_k1_stream_pointwise_only(ip, seg_rows, dtype):
+    """threshold <= 0 (no artefact step, no nan_to_num) through the streaming pipeline: 0 ulp of the float64 result at
+    every segment seam, with finite and non-finite calibration values, several frames per launch"""
+    H, W, n = 61, 272, 3
+    _, dark, flat = _case(H, W, 8)
+    frames = np.stack([synth.scene(H, W, 40 + i, dtype) for i in range(n)])
+    e = _eng(ip, H, W, 3)
+    e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, seg_rows)
+    try:
+        for d, f in ((dark, flat), (np.where(dark > 105, np.inf, dark).astype(np.float32), np.where(flat > 0.9, np.nan, flat).astype(np.float32))):
+            e.set_dark(d)
+            e.set_flat(f)
+            out, _ = e.pointwise_median(_dev(frames), 0.0, 3, flags=ip.lib_mod.DO_DARK | ip.lib_mod.DO_FLAT)
+            for i in range(n):
+                with np.errstate(all='ignore'):
+                    want = models.pointwise_model(frames[i], d, f, False)
+                assert np.array_equal(out[i].cpu().numpy(), want, equal_nan=True), (seg_rows, dtype, i)
+    finally:
+        e.set_option(ip.lib_mod.OPT_K1_SEG_ROWS, 0)
+        e.set_option(ip.lib_mod.OPT_K1_VARIANT, 0)
+
+
 def test_k1_multi_frame_batch(ip):
     H, W, n = 70, 272, 5
     e = _eng(ip, H, W, 0)
