@@ -63,7 +63,7 @@ enum {
 /* imgcorr_set_option keys */
 enum {
     IMGCORR_OPT_K1_VARIANT = 1, /* 0 auto, 1 generic tiles, 2 TMA-staged tiles, 3 / 4 TMA streaming pipeline v1 (3x3 and 5x5) / v2 (3x3, two columns per lane) (2-4 fail if not eligible) */
-    IMGCORR_OPT_K2_VARIANT = 2, /* 0 auto, 1 gathers through L1/L2, 2 shared-memory staged tiles (float32 sources; fails if not eligible) */
+    IMGCORR_OPT_K2_VARIANT = 2, /* 0 auto, 1 gathers through L1/L2, 2 shared-memory staged tiles (float32 / uint16 / uint8 sources; fails if not eligible) */
     IMGCORR_OPT_HOST_SLOTS = 3, /* depth of the pinned / device staging ring of the *_host calls (default 4) */
     IMGCORR_OPT_K1_SEG_ROWS = 4, /* rows per work unit of the streaming K1 kernel (0 = default) */
     IMGCORR_OPT_PROFILE = 5,     /* n > 0: bracket the K1 and K2 launch of every n-th frame group of the chain with CUDA

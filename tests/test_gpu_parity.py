@@ -457,6 +457,33 @@ def test_k2_variants_bit_identical(ip, k2_variant, lens_kind):
         e.set_option(ip.lib_mod.OPT_K2_VARIANT, 0)
 
 
+@pytest.mark.parametrize('k2_variant', [0, 1, 2])
+@pytest.mark.parametrize('dtype', [np.uint16, np.uint8])
+def test_k2_integer_frames_all_variants(ip, k2_variant, dtype):
+    """uint16 / uint8 frames (int16 fixed-point weights for uint8) through L1 gathers, the staged tiles and the automatic
+    choice (tiles from 4 frames per launch): bit-exact vs the model, border value rounded to the image type, roi window"""
+    H, W = 200, 336                                             # 336 uint8 columns = 21 x 16 bytes: tiles eligible for both types
+    p = synth.lens_moderate(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    mapx, mapy, P, roi = refpath.undistort_rectify_map(K, d, W, H)
+    e = _eng(ip, H, W)
+    e.set_lens(K, d, P)
+    e.set_option(ip.lib_mod.OPT_K2_VARIANT, k2_variant)
+    try:
+        mx, my = (m.cpu().numpy() for m in e.undistort_maps())
+        x, y, w, h = (int(v) for v in roi)
+        for n in (1, 6):
+            frames = np.stack([synth.scene(H, W, 60 + i, dtype) for i in range(n)])
+            full = e.undistort(_dev(frames), border_value=77.6).cpu().numpy()
+            crop = e.undistort(_dev(frames), window=(x, y, w, h)).cpu().numpy()
+            assert full.dtype == dtype
+            for i in range(n):
+                assert np.array_equal(full[i], models.remap_model(frames[i], mx, my, 77.6)), (k2_variant, dtype, n, i)
+                assert np.array_equal(crop[i], models.remap_model(frames[i], mx, my, 0.0)[y:y + h, x:x + w])
+    finally:
+        e.set_option(ip.lib_mod.OPT_K2_VARIANT, 0)
+
+
 def test_undistort_multi_frame_and_window(ip):
     H, W, n = 125, 166, 4
     p = synth.lens_moderate(H, W)
