@@ -7,6 +7,10 @@
 //   medianThreshold(image, thr, size)        filters/medianThreshold.py:7-30
 // with one pass over HBM: raw (2 or 4 B/px) + dark (4) + flat (4) in, corrected float32 (4) out.
 //
+// This file holds the tile kernels and the dispatcher (launch_k1).  The default paths are the streaming pipelines in
+// k1_stream.cu (3x3, and threshold <= 0) and k1_stream5.cu (5x5); the tiles below serve the shapes / dtypes / options
+// those do not take (odd widths, float64 frames, the legacy linear dark model, framed file images).
+//
 // Two staging variants share the same compute phases:
 //   generic : coalesced ld.global.nc with reflect indexing (any W, any alignment, any dtype)
 //   tma     : persistent CTAs, cp.async.bulk.tensor tiles (+halo) of raw/dark/flat into a
