@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "../../include/imgcorr.h"
@@ -700,8 +701,15 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
     if (out_dtype != DT_F32 && out_dtype != DT_F64) return fail(IMGCORR_ERR_INVALID, "out_dtype must be F32 or F64");
     const bool lens = use_lens && c->has_lens;
     if (!lens) { x0 = 0; y0 = 0; ow = c->W; oh = c->H; }
-    const size_t raw_bytes = (size_t)c->H * c->W * dtype_size(raw_dtype);
-    const size_t out_bytes = (size_t)ow * oh * dtype_size(out_dtype);
+    const size_t frame_raw = (size_t)c->H * c->W * dtype_size(raw_dtype);
+    const size_t frame_out = (size_t)ow * oh * dtype_size(out_dtype);
+    // small frames travel in chunks of G frames per ring slot (up to 32 MB of raw data, at most 16 frames): one copy each
+    // way and one K1 / K2 launch per chunk instead of per frame; frames above 16 MB (the 4096x3000 workload) keep one
+    // frame per slot
+    int G = 1;
+    if (frame_raw <= ((size_t)16 << 20)) G = (int)std::min<size_t>(16, ((size_t)32 << 20) / frame_raw);
+    if (G > n_frames) G = n_frames > 0 ? n_frames : 1;
+    const size_t raw_bytes = frame_raw * G, out_bytes = frame_out * G;
     int r = ensure_pipeline(c, raw_bytes, out_bytes);
     if (r) return r;
     const bool in_pinned = is_pinned(raw_host), out_pinned = is_pinned(out_host);
@@ -710,30 +718,33 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
         if (!out_pinned && !s.h_out) CK(cudaHostAlloc(&s.h_out, c->slot_out_bytes, cudaHostAllocDefault));
     }
     const int ns = (int)c->slots.size();
-    auto retire = [&](int frame) -> int {      // frame's D2H has been enqueued on s_out in slot frame % ns
-        HostSlot& s = c->slots[frame % ns];
+    const int chunks = (n_frames + G - 1) / G;
+    auto frames_of = [&](int k) { return n_frames - k * G < G ? n_frames - k * G : G; };
+    auto retire = [&](int k) -> int {          // chunk k's D2H has been enqueued on s_out in slot k % ns
+        HostSlot& s = c->slots[k % ns];
         CK(cudaEventSynchronize(s.ev_out));
-        if (!out_pinned) memcpy((char*)out_host + (size_t)frame * out_bytes, s.h_out, out_bytes);
+        if (!out_pinned) memcpy((char*)out_host + (size_t)k * out_bytes, s.h_out, frame_out * frames_of(k));
         return IMGCORR_OK;
     };
-    for (int f = 0; f < n_frames; ++f) {
-        HostSlot& s = c->slots[f % ns];
-        if (f >= ns) { r = retire(f - ns); if (r) return r; }
-        const char* src = (const char*)raw_host + (size_t)f * raw_bytes;
-        if (!in_pinned) { memcpy(s.h_raw, src, raw_bytes); src = (const char*)s.h_raw; }
-        CK(cudaMemcpyAsync(s.d_raw, src, raw_bytes, cudaMemcpyHostToDevice, c->s_in));
+    for (int k = 0; k < chunks; ++k) {
+        HostSlot& s = c->slots[k % ns];
+        if (k >= ns) { r = retire(k - ns); if (r) return r; }
+        const int nf = frames_of(k);
+        const char* src = (const char*)raw_host + (size_t)k * raw_bytes;
+        if (!in_pinned) { memcpy(s.h_raw, src, frame_raw * nf); src = (const char*)s.h_raw; }
+        CK(cudaMemcpyAsync(s.d_raw, src, frame_raw * nf, cudaMemcpyHostToDevice, c->s_in));
         CK(cudaEventRecord(s.ev_in, c->s_in));
         CK(cudaStreamWaitEvent(c->s_k, s.ev_in, 0));
-        r = chain_frames(c, s.d_raw, raw_dtype, s.d_out, out_dtype, 1, threshold, ksize, flags, lens, border_value, x0, y0,
+        r = chain_frames(c, s.d_raw, raw_dtype, s.d_out, out_dtype, nf, threshold, ksize, flags, lens, border_value, x0, y0,
                          ow, oh, c->s_k);
         if (r) return r;
         CK(cudaEventRecord(s.ev_k, c->s_k));
         CK(cudaStreamWaitEvent(c->s_out, s.ev_k, 0));
-        void* dst = out_pinned ? (void*)((char*)out_host + (size_t)f * out_bytes) : s.h_out;
-        CK(cudaMemcpyAsync(dst, s.d_out, out_bytes, cudaMemcpyDeviceToHost, c->s_out));
+        void* dst = out_pinned ? (void*)((char*)out_host + (size_t)k * out_bytes) : s.h_out;
+        CK(cudaMemcpyAsync(dst, s.d_out, frame_out * nf, cudaMemcpyDeviceToHost, c->s_out));
         CK(cudaEventRecord(s.ev_out, c->s_out));
     }
-    for (int f = (n_frames > ns ? n_frames - ns : 0); f < n_frames; ++f) { r = retire(f); if (r) return r; }
+    for (int k = (chunks > ns ? chunks - ns : 0); k < chunks; ++k) { r = retire(k); if (r) return r; }
     return IMGCORR_OK;
 }
 

@@ -150,7 +150,7 @@ IMGCORR_API int imgcorr_correct_batch(imgcorr_ctx* ctx, const void* raw_dev, int
                           int x0, int y0, int ow, int oh, void* stream);
 
 /* Same chain with HOST buffers: frames are staged through a ring of pinned buffers, H2D copy,
- * kernels and D2H copy of consecutive frames overlap on three streams.  Synchronous: returns
+ * kernels and D2H copy of consecutive frames (small frames: chunks of up to 16 frames) overlap on three streams.  Synchronous: returns
  * when out_host is complete.  Fastest when raw_host / out_host come from imgcorr_host_alloc
  * (or are otherwise page-locked). */
 IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* ctx, const void* raw_host, int raw_dtype, void* out_host, int out_dtype,

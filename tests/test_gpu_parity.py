@@ -640,6 +640,28 @@ def test_correct_batch_device_and_host(ip):
     assert r is pin_out and np.array_equal(pin_out.astype(np.float64), single[:, y:y + h, x:x + w])
 
 
+def test_correct_host_chunks_small_frames(ip):
+    """small frames go through the host pipeline in chunks of up to 16 per ring slot: more chunks than slots, a ragged last
+    chunk, pinned and pageable buffers — same output as the device-resident chain"""
+    H, W, n = 96, 128, 103
+    g = load_golden('correct_u16_keep1')
+    cal = _cal(ip, g)
+    _quiet(cal.correct, g['raw'], threshold=0.1)                         # uploads the calibration into the engine
+    e = ip.engine_mod.get_engine(H, W)
+    rng = np.random.default_rng(8)
+    frames = (synth.scene(H, W, 70, np.uint16)[None].astype(np.int64) + rng.integers(-200, 200, (n, H, W))).clip(0, 65535).astype(np.uint16)
+    want = e.correct_batch(_dev(frames), threshold=0.1).cpu().numpy()
+    got = e.correct_host(frames, threshold=0.1)                          # pageable
+    assert np.array_equal(got, want)
+    pin_in = ip.engine_mod.pinned_empty(frames.shape, np.uint16)
+    pin_out = ip.engine_mod.pinned_empty(frames.shape, np.float32)
+    pin_in[...] = frames
+    pin_out[...] = -1
+    e.correct_host(pin_in, out=pin_out, threshold=0.1)
+    assert np.array_equal(pin_out, want)
+    assert np.array_equal(e.correct_host(frames[:5], threshold=0.1), want[:5])     # fewer frames than one chunk
+
+
 def test_calibration_modified_in_place_is_uploaded_again(ip):
     """the reference reads its calibration arrays on every call; the engine's upload cache must notice an in-place edit"""
     g = dict(load_golden('correct_u16_keep1'))
