@@ -2,8 +2,8 @@
 // warp-specialised TMA pipeline with the stencil window held in registers.
 //
 //   * work unit = (frame, 120-column strip, segment of rows).  A CTA is 4 consumer warps + 1 producer
-//     warp and walks its units top to bottom in chunks of 8 rows.
-//   * the producer warp (one elected lane) fills a 4-stage shared-memory ring with
+//     warp and walks its units top to bottom in chunks of 32 rows.
+//   * the producer warp (one elected lane) fills a 2-stage shared-memory ring with
 //     cp.async.bulk.tensor boxes of raw / dark / flat rows (16-byte aligned, 16-byte multiple wide,
 //     out-of-frame parts zero-filled by TMA), signalled through `full` mbarriers; consumers hand a
 //     stage back through `empty` mbarriers.  There is no CTA-wide barrier in the steady state.
@@ -24,32 +24,28 @@ namespace imgcorr {
 constexpr int KS_CW = 4;                    // consumer warps per CTA
 constexpr int KS_SW = 30;                   // output columns per consumer warp
 constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
-#ifndef KS_R_V
-#define KS_R_V 8
-#endif
-#ifndef KS_NSTAGE_V
-#define KS_NSTAGE_V 4
-#endif
-#ifndef KS_MINB_V
-#define KS_MINB_V 5
-#endif
-constexpr int KS_R = KS_R_V;                // rows per pipeline stage
-constexpr int KS_NSTAGE = KS_NSTAGE_V;
-constexpr int KS_MINB = KS_MINB_V;          // CTAs per SM the register allocation aims at
+// Pipeline shape: rows per stage x stages x CTAs per SM the register allocation aims at.  Measured on B200 (4096x3000
+// uint16, 32 frames per launch): 8 x 4 x 5 (72 registers) 34.5 us/frame; 16 x 3 x 3 32.8; 24 x 3 x 2 30.9; 32 x 2 x 2 (124
+// registers) 30.6 — long straight-line chunks with many independent rows in flight per warp beat occupancy, the kernel is
+// bound by dependent-issue latency, not by any pipe.  With few frames per launch (one frame: 57 vs 44 us) and for the
+// integer-output instantiations (uint16 medianThreshold: 52 vs 41 us/frame) the small shape wins, so both are built.
+template <int R_, int NSTAGE_, int MINB_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_; };
+typedef KsShape<8, 4, 5> KsNarrow;
+typedef KsShape<32, 2, 3> KsWide;
 constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
 constexpr int KS_MAPX = 4;
 constexpr int KS_THREADS = (KS_CW + 1) * 32;
 
-template <typename RawT> struct StreamBox {
+template <typename RawT, typename C> struct StreamBox {
     static constexpr int XOFF = 16 / (int)sizeof(RawT);                        // u8 16, u16 8, f32 4
     static constexpr int GRAN = 16 / (int)sizeof(RawT);
     // the box starts at the 16-byte boundary at or left of tx0, minus XOFF: columns tx0-1 .. tx0+120 are inside
     static constexpr int BOXW = ((KS_TW + 2 * XOFF + GRAN - 1) / GRAN) * GRAN;  // u8 160, u16 136, f32 128
-    static constexpr size_t raw_bytes = (size_t)KS_R * BOXW * sizeof(RawT);     // multiples of 128
-    static constexpr size_t map_bytes = (size_t)KS_R * KS_MAPW * sizeof(float);
+    static constexpr size_t raw_bytes = (size_t)C::R * BOXW * sizeof(RawT);     // multiples of 128
+    static constexpr size_t map_bytes = (size_t)C::R * KS_MAPW * sizeof(float);
     static constexpr size_t stage_bytes = raw_bytes + 2 * map_bytes;
-    static constexpr size_t bar_off = KS_NSTAGE * stage_bytes;
-    static constexpr size_t total = bar_off + 2 * KS_NSTAGE * sizeof(uint64_t) + 64;
+    static constexpr size_t bar_off = C::NSTAGE * stage_bytes;
+    static constexpr size_t total = bar_off + 2 * C::NSTAGE * sizeof(uint64_t) + 64;
 };
 
 template <typename T> struct StreamRaw;
@@ -71,6 +67,7 @@ __device__ __noinline__ bool ks_exact(float x, float b, double thr, int cond) {
 struct UnitGeom {
     int frame, tx0, ys, ye, yl0, n_in, nchunk;
 };
+template <int R>
 __device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int seg_rows, int H, int n_frames) {
     // frame index fastest: the units that share the dark / flat rows of one (strip, segment) run back to back,
     // so those rows are read from DRAM once per launch and served from L2 for the other frames
@@ -86,7 +83,7 @@ __device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int 
     u.yl0 = u.ys > 0 ? u.ys - 1 : 0;
     const int yl1 = u.ye < H ? u.ye : H - 1;
     u.n_in = yl1 - u.yl0 + 1;
-    u.nchunk = (u.n_in + KS_R - 1) / KS_R;
+    u.nchunk = (u.n_in + R - 1) / R;
     return u;
 }
 
@@ -99,11 +96,12 @@ enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, K
 // KS_NZ: a.flat is the zero-free copy (zeros replaced by 1.0) -> unconditional division
 // KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
 
-template <typename RawT, typename OutT, int CFG>
-__global__ void __launch_bounds__(KS_THREADS, KS_MINB)
+template <typename RawT, typename OutT, int CFG, typename C>
+__global__ void __launch_bounds__(KS_THREADS, C::MINB)
 k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_dark,
                  const __grid_constant__ CUtensorMap tm_flat, K1Args a, int strips, int segs, int seg_rows, int total_units) {
-    using B = StreamBox<RawT>;
+    using B = StreamBox<RawT, C>;
+    constexpr int KS_R = C::R, KS_NSTAGE = C::NSTAGE;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = (uint64_t*)(smem + B::bar_off);
     uint64_t* empty = full + KS_NSTAGE;
@@ -132,7 +130,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
         const uint32_t tx_bytes = (uint32_t)(B::raw_bytes + (has_dark ? B::map_bytes : 0) + (has_flat ? B::map_bytes : 0));
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const UnitGeom u = ks_unit(unit, strips, segs, seg_rows, H, a.n_frames);
+            const UnitGeom u = ks_unit<KS_R>(unit, strips, segs, seg_rows, H, a.n_frames);
             for (int k = 0; k < u.nchunk; ++k, ++g) {
                 const int stage = g % KS_NSTAGE;
                 mbar_wait(&empty[stage], ((g / KS_NSTAGE) & 1) ^ 1);
@@ -157,7 +155,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     uint32_t g = 0;
 
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const UnitGeom u = ks_unit(unit, strips, segs, seg_rows, H, a.n_frames);
+        const UnitGeom u = ks_unit<KS_R>(unit, strips, segs, seg_rows, H, a.n_frames);
         const int gc = u.tx0 + lc;
         const int rc = reflect_index(gc, W);             // scipy 'reflect' in x: halo / outside lanes read the mirrored column
         int mcol = rc - (u.tx0 - KS_MAPX);
@@ -304,9 +302,10 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     return tensor_map_encoder() != nullptr;
 }
 
-template <typename RawT, typename OutT>
-static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
-    using B = StreamBox<RawT>;
+template <typename RawT, typename OutT, typename C>
+static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
+    using B = StreamBox<RawT, C>;
+    constexpr int KS_R = C::R;
     K1Args a = a_in;
     // pick the instantiation: the hot configurations are fully specialised, the rest read their flags at run time
     const bool check = !a.maps_finite || sizeof(RawT) == 4;
@@ -320,19 +319,19 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     const bool pw_only = a.ksize == 0 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && !a.raw_swap && !check;
     if (chain || pw_only) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
     if (pw_only) {
-        kern = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_NOMED>
-                                                       : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_NOMED>;
+        kern = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_NOMED, C>
+                                                       : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_NOMED, C>;
         slot = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? 7 : 8;
     } else if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
-        kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP>
-                             : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP>;
+        kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP, C>
+                             : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP, C>;
         slot = a.no_overflow ? 5 : 6;
-    } else if (a.raw_swap) { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 4; if (chain) a.flat = a_in.flat; }
-    else if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ>; slot = 0; }
-    else if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ>; slot = 1; }
-    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK>; slot = 2; }
-    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK>; slot = 3; }
-    else { kern = k1_stream_kernel<RawT, OutT, -1>; slot = 4; }
+    } else if (a.raw_swap) { kern = k1_stream_kernel<RawT, OutT, -1, C>; slot = 4; if (chain) a.flat = a_in.flat; }
+    else if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ, C>; slot = 0; }
+    else if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ, C>; slot = 1; }
+    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK, C>; slot = 2; }
+    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK, C>; slot = 3; }
+    else { kern = k1_stream_kernel<RawT, OutT, -1, C>; slot = 4; }
 
     CUtensorMap tr, td, tf;
     if (!make_tensor_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
@@ -375,6 +374,13 @@ static cudaError_t launch_stream_t(const K1Args& a_in, CUtensorMapDataType rdt, 
     if (grid > total) grid = total;
     kern<<<(unsigned)grid, KS_THREADS, B::total, st>>>(tr, td, tf, a, strips, segs, seg_rows, (int)total);
     return cudaGetLastError();
+}
+
+template <typename RawT, typename OutT>
+static cudaError_t launch_stream_t(const K1Args& a, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
+    // the wide shape pays with float32 output and a few frames per launch (see KsShape)
+    if (sizeof(OutT) == 4 && a.n_frames >= 4) return launch_stream_c<RawT, OutT, KsWide>(a, rdt, sm_count, seg_rows, st);
+    return launch_stream_c<RawT, OutT, KsNarrow>(a, rdt, sm_count, seg_rows, st);
 }
 
 cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t st) {

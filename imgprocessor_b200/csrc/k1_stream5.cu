@@ -40,8 +40,14 @@ constexpr int K5_TW = K5_CW * K5_SW;        // 112 output columns per strip
 #ifndef K5_MINB_V
 #define K5_MINB_V 3
 #endif
-constexpr int K5_R = 8;                     // rows per pipeline stage
-constexpr int K5_NSTAGE = 4;
+#ifndef K5_R_V
+#define K5_R_V 8
+#endif
+#ifndef K5_NSTAGE_V
+#define K5_NSTAGE_V 4
+#endif
+constexpr int K5_R = K5_R_V;                // rows per pipeline stage
+constexpr int K5_NSTAGE = K5_NSTAGE_V;
 constexpr int K5_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
 constexpr int K5_MAPX = 4;
 constexpr int K5_THREADS = (K5_CW + 1) * 32;
