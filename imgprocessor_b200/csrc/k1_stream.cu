@@ -31,7 +31,11 @@ constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
 // integer-output instantiations (uint16 medianThreshold: 52 vs 41 us/frame) the small shape wins, so both are built.
 template <int R_, int NSTAGE_, int MINB_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_; };
 typedef KsShape<8, 4, 5> KsNarrow;
-typedef KsShape<32, 2, 3> KsWide;
+#ifndef KS_WIDE_R
+#define KS_WIDE_R 32
+#define KS_WIDE_MINB 3
+#endif
+typedef KsShape<KS_WIDE_R, 2, KS_WIDE_MINB> KsWide;
 constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
 constexpr int KS_MAPX = 4;
 constexpr int KS_THREADS = (KS_CW + 1) * 32;
