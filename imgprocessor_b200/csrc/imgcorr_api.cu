@@ -174,7 +174,7 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
     if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
     switch (key) {
         case IMGCORR_OPT_K1_VARIANT:
-            if (value < 0 || value > 4) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
+            if (value < 0 || value > 3) return fail(IMGCORR_ERR_INVALID, "k1 variant %d", value);
             c->k1_variant = value;
             return IMGCORR_OK;
         case IMGCORR_OPT_K2_VARIANT:
@@ -745,6 +745,25 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
         CK(cudaEventRecord(s.ev_out, c->s_out));
     }
     for (int k = (chunks > ns ? chunks - ns : 0); k < chunks; ++k) { r = retire(k); if (r) return r; }
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_selftest_division(imgcorr_ctx* c, int numerators_per_divisor, unsigned long long seed, double out[2]) {
+    GUARD(c);
+    if (!out || numerators_per_divisor < 1) return fail(IMGCORR_ERR_INVALID, "bad self-test arguments");
+    unsigned long long* d = nullptr;
+    unsigned long long h[2] = {0, 0};
+    CK(cudaMalloc((void**)&d, sizeof h));
+    cudaError_t e = cudaMemset(d, 0, sizeof h);
+    if (e == cudaSuccess) e = launch_selftest_division(numerators_per_divisor, seed, d, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return cuda_fail(e, "division self-test");
+    c->launches += 1;
+    out[0] = (double)h[0];
+    double worst;
+    memcpy(&worst, &h[1], sizeof worst);
+    out[1] = worst;
     return IMGCORR_OK;
 }
 

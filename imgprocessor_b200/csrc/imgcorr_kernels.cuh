@@ -34,7 +34,7 @@ struct K1Args {
 };
 
 // variant: 0 = pick automatically, 1 = generic tiles (plain coalesced loads), 2 = TMA-staged tiles,
-//          3 = TMA streaming pipeline (3x3 only), 4 = streaming pipeline v2 (two columns per lane; u16 / f32, 3x3).  seg_rows: rows per work unit of the streaming kernel (0 = default)
+//          3 = TMA streaming pipeline (3x3 and 5x5).  seg_rows: rows per work unit of the streaming kernel (0 = default)
 cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count, int seg_rows,
                       cudaStream_t stream, int* launches);
 bool k1_tma_eligible(const K1Args& a, int raw_dtype, int out_dtype);
@@ -42,8 +42,6 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype);
 cudaError_t launch_k1_stream(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 bool k1_stream5_eligible(const K1Args& a, int raw_dtype, int out_dtype);     // 5x5 streaming pipeline
 cudaError_t launch_k1_stream5(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
-bool k1_stream2_eligible(const K1Args& a, int raw_dtype, int out_dtype);
-cudaError_t launch_k1_stream2(const K1Args& a, int raw_dtype, int out_dtype, int sm_count, int seg_rows, cudaStream_t stream);
 
 // K2: undistortion remap ---------------------------------------------------------------------
 struct K2Args {
@@ -93,5 +91,8 @@ struct K4Args {
     SteConst sc;
 };
 cudaError_t launch_k4(const K4Args& a, int dtype, cudaStream_t stream, int* launches);
+
+// device self-test of the float64 division sequence (selftest.cu); dev2 = {mismatches, bits of the worst seed error}
+cudaError_t launch_selftest_division(int nnum, uint64_t seed, unsigned long long* dev2, cudaStream_t stream);
 
 }  // namespace imgcorr

@@ -464,14 +464,6 @@ static cudaError_t dispatch_ks(const K1Args& a, bool tma, CUtensorMapDataType rd
 cudaError_t launch_k1(const K1Args& a, int raw_dtype, int out_dtype, int variant, int sm_count, int seg_rows,
                       cudaStream_t st, int* launches) {
     if (a.n_frames <= 0 || a.H <= 0 || a.W <= 0) return cudaSuccess;
-    // streaming v2 (two columns per lane) issues fewer instructions per pixel but measured slower than v1 on B200
-    // (profiles/): it stays selectable (variant 4) and tested, automatic dispatch prefers v1.
-    const bool s2_ok = variant == 4 && k1_stream2_eligible(a, raw_dtype, out_dtype);
-    if (variant == 4 && !s2_ok) return cudaErrorNotSupported;
-    if (s2_ok) {
-        if (launches) ++*launches;
-        return launch_k1_stream2(a, raw_dtype, out_dtype, sm_count, seg_rows, st);
-    }
     const bool stream_ok = (variant == 0 || variant == 3) && k1_stream_eligible(a, raw_dtype, out_dtype);
     const bool stream5_ok = (variant == 0 || variant == 3) && k1_stream5_eligible(a, raw_dtype, out_dtype);
     if (variant == 3 && !stream_ok && !stream5_ok) return cudaErrorNotSupported;

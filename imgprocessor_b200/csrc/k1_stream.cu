@@ -1,41 +1,56 @@
 // K1, streaming variant (3x3): the fused dark / flat / nan_to_num / median-threshold kernel as a
 // warp-specialised TMA pipeline with the stencil window held in registers.
 //
-//   * work unit = (frame, 120-column strip, segment of rows).  A CTA is 4 consumer warps + 1 producer
-//     warp and walks its units top to bottom in chunks of 32 rows.
-//   * the producer warp (one elected lane) fills a 2-stage shared-memory ring with
-//     cp.async.bulk.tensor boxes of raw / dark / flat rows (16-byte aligned, 16-byte multiple wide,
+//   * work unit = (group of NF frames, 120-column strip, segment of rows).  A CTA is 4 consumer warps + 1 producer
+//     warp and walks its units top to bottom in chunks of R rows.
+//   * the producer warp (one elected lane) fills a shared-memory ring with cp.async.bulk.tensor boxes of
+//     raw (one per frame of the group) / dark / flat rows (16-byte aligned, 16-byte multiple wide,
 //     out-of-frame parts zero-filled by TMA), signalled through `full` mbarriers; consumers hand a
 //     stage back through `empty` mbarriers.  There is no CTA-wide barrier in the steady state.
 //   * each consumer lane owns one image column of its warp's 30-column slice (+1 halo lane on each
 //     side; the halo / out-of-frame lanes read the mirrored column, which is scipy's 'reflect').
-//     Per row it reads raw, dark, flat from shared memory, computes the pointwise value in float64
-//     registers (one rounding to float32), fetches the left / right neighbours with two warp shuffles,
-//     sorts the horizontal triple and combines it with the two previous rows' triples (kept in
-//     registers) into the median of 9; predicate + select + one coalesced store per row.
+//     Per row it reads dark and flat once, turns the flat value into a float64 reciprocal once (MUFU seed + one Newton
+//     step) and applies both to the raw sample of every frame of the group: float64 subtraction, reciprocal multiply,
+//     residual correction (= the correctly rounded float64 quotient, imgcorr_core.cuh), one rounding to float32.  The
+//     frame-independent half of the division is thereby shared by the NF frames (NF = 2 for batches).
+//   * per frame: left / right neighbours with two warp shuffles, a 3-element sort of the horizontal triple, and — two
+//     output rows at a time — the median of 9 from the sorted triples of four consecutive rows (the two middle rows'
+//     contribution is computed once for both outputs); predicate + select + one coalesced store per row.
 //   * vertical 'reflect' needs no halo rows: the first / last row's sorted triple is used twice.
 //
 // Same arithmetic as the tile kernels (imgcorr_core.cuh) — results are bit-identical.
 #include "imgcorr_kernels.cuh"
 #include "imgcorr_tma.cuh"
+#include <mutex>
 
 namespace imgcorr {
 
 constexpr int KS_CW = 4;                    // consumer warps per CTA
 constexpr int KS_SW = 30;                   // output columns per consumer warp
 constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
-// Pipeline shape: rows per stage x stages x CTAs per SM the register allocation aims at.  Measured on B200 (4096x3000
-// uint16, 32 frames per launch): 8 x 4 x 5 (72 registers) 34.5 us/frame; 16 x 3 x 3 32.8; 24 x 3 x 2 30.9; 32 x 2 x 2 (124
-// registers) 30.6 — long straight-line chunks with many independent rows in flight per warp beat occupancy, the kernel is
-// bound by dependent-issue latency, not by any pipe.  With few frames per launch (one frame: 57 vs 44 us) and for the
-// integer-output instantiations (uint16 medianThreshold: 52 vs 41 us/frame) the small shape wins, so both are built.
-template <int R_, int NSTAGE_, int MINB_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_; };
-typedef KsShape<8, 4, 5> KsNarrow;
+// Pipeline shape: rows per stage x stages x CTAs per SM the register allocation aims at x frames per work unit.
+// Long straight-line chunks with many independent rows in flight per warp beat occupancy (round 1: 8 x 4 x 5 34.5 us per
+// 4096x3000 frame, 32 x 2 x 2 30.6); with few frames per launch and for the integer-output instantiations the small shape
+// wins, so both are built.  Batches of float32-output frames run two frames per unit (KsPair).
+template <int R_, int NSTAGE_, int MINB_, int NF_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_, NF = NF_; };
+#ifndef KS_NARROW_R
+#define KS_NARROW_R 8
+#define KS_NARROW_NSTAGE 4
+#define KS_NARROW_MINB 5
+#endif
+typedef KsShape<KS_NARROW_R, KS_NARROW_NSTAGE, KS_NARROW_MINB, 1> KsNarrow;
 #ifndef KS_WIDE_R
 #define KS_WIDE_R 32
+#define KS_WIDE_NSTAGE 2
 #define KS_WIDE_MINB 3
 #endif
-typedef KsShape<KS_WIDE_R, 2, KS_WIDE_MINB> KsWide;
+typedef KsShape<KS_WIDE_R, KS_WIDE_NSTAGE, KS_WIDE_MINB, 1> KsWide;
+#ifndef KS_PAIR_R
+#define KS_PAIR_R 16
+#define KS_PAIR_NSTAGE 3
+#define KS_PAIR_MINB 2
+#endif
+typedef KsShape<KS_PAIR_R, KS_PAIR_NSTAGE, KS_PAIR_MINB, 2> KsPair;
 constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
 constexpr int KS_MAPX = 4;
 constexpr int KS_THREADS = (KS_CW + 1) * 32;
@@ -47,7 +62,7 @@ template <typename RawT, typename C> struct StreamBox {
     static constexpr int BOXW = ((KS_TW + 2 * XOFF + GRAN - 1) / GRAN) * GRAN;  // u8 160, u16 136, f32 128
     static constexpr size_t raw_bytes = (size_t)C::R * BOXW * sizeof(RawT);     // multiples of 128
     static constexpr size_t map_bytes = (size_t)C::R * KS_MAPW * sizeof(float);
-    static constexpr size_t stage_bytes = raw_bytes + 2 * map_bytes;
+    static constexpr size_t stage_bytes = C::NF * raw_bytes + 2 * map_bytes;    // raw[NF] | dark | flat
     static constexpr size_t bar_off = C::NSTAGE * stage_bytes;
     static constexpr size_t total = bar_off + 2 * C::NSTAGE * sizeof(uint64_t) + 64;
 };
@@ -71,16 +86,15 @@ __device__ __noinline__ bool ks_exact(float x, float b, double thr, int cond) {
 struct UnitGeom {
     int frame, tx0, ys, ye, yl0, n_in, nchunk;
 };
-template <int R>
-__device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int segs, int seg_rows, int H, int n_frames) {
-    // frame index fastest: the units that share the dark / flat rows of one (strip, segment) run back to back,
+template <int R, int NF>
+__device__ __forceinline__ UnitGeom ks_unit(int unit, int strips, int seg_rows, int H, int n_groups) {
+    // frame group fastest: the units that share the dark / flat rows of one (strip, segment) run back to back,
     // so those rows are read from DRAM once per launch and served from L2 for the other frames
     UnitGeom u;
-    u.frame = unit % n_frames;
-    int t = unit / n_frames;
+    u.frame = (unit % n_groups) * NF;
+    int t = unit / n_groups;
     const int strip = t % strips;
     const int seg = t / strips;
-    (void)segs;
     u.tx0 = strip * KS_TW;
     u.ys = seg * seg_rows;
     u.ye = u.ys + seg_rows < H ? u.ys + seg_rows : H;
@@ -100,12 +114,37 @@ enum : int { KS_DARK = 1, KS_FLAT = 2, KS_N2N = 4, KS_MASK = 8, KS_CHECK = 16, K
 // KS_NZ: a.flat is the zero-free copy (zeros replaced by 1.0) -> unconditional division
 // KS_CHECK: non-finite calibration values or float32 raw samples are possible -> test and fall back per pixel
 
+// dark / flat of one pixel position, prepared once for all frames of the unit
+struct RowMaps {
+    float d, f;
+    double dd, fd, y;       // float64 copies and the refined reciprocal of the (zero-free) flat value
+};
+
+// medians of two vertically adjacent 3x3 windows from the sorted horizontal triples of four consecutive rows a, b, c, e:
+// window 1 = rows (a, b, c), window 2 = rows (b, c, e).  The contribution of the shared rows b, c to the "median of the
+// mids" is one ordered pair; max of the lows / min of the highs are single 3-input FMNMX3.  15 min/max per output pixel
+// including the sort of the new row (16 with independent windows).
+__device__ __forceinline__ void median9_pair(const Sorted3<float>& a, const Sorted3<float>& b, const Sorted3<float>& c,
+                                             const Sorted3<float>& e, float& m1, float& m2) {
+    const float mlo = vmin(b.mid, c.mid), mhi = vmax(b.mid, c.mid);
+    const float mid1 = vmax(mlo, vmin(mhi, a.mid));
+    const float mid2 = vmax(mlo, vmin(mhi, e.mid));
+    const float lo1 = vmax(vmax(a.lo, b.lo), c.lo), hi1 = vmin(vmin(a.hi, b.hi), c.hi);
+    const float lo2 = vmax(vmax(b.lo, c.lo), e.lo), hi2 = vmin(vmin(b.hi, c.hi), e.hi);
+    m1 = med3(lo1, mid1, hi1);
+    m2 = med3(lo2, mid2, hi2);
+}
+
 template <typename RawT, typename OutT, int CFG, typename C>
 __global__ void __launch_bounds__(KS_THREADS, C::MINB)
 k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_constant__ CUtensorMap tm_dark,
-                 const __grid_constant__ CUtensorMap tm_flat, K1Args a, int strips, int segs, int seg_rows, int total_units) {
+                 const __grid_constant__ CUtensorMap tm_flat, K1Args a, int strips, int seg_rows, int total_units) {
     using B = StreamBox<RawT, C>;
-    constexpr int KS_R = C::R, KS_NSTAGE = C::NSTAGE;
+    constexpr int KS_R = C::R, KS_NSTAGE = C::NSTAGE, NF = C::NF;
+    static_assert(KS_R % 2 == 0, "rows per stage must be even (outputs are produced in vertical pairs)");
+    static_assert(NF == 1 || (CFG >= 0 && !(CFG & KS_MASK)), "multi-frame units: specialised configurations without a mask only");
+    // the frame-independent half of the division is hoisted whenever the flat value is known to be non-zero
+    constexpr bool FASTDIV = CFG >= 0 && (CFG & KS_NZ) && (CFG & KS_DARK) && (CFG & KS_FLAT);
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = (uint64_t*)(smem + B::bar_off);
     uint64_t* empty = full + KS_NSTAGE;
@@ -119,6 +158,7 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     const int flags = CFG >= 0 ? ((CFG & KS_DARK ? FLAG_DARK : 0) | (CFG & KS_FLAT ? FLAG_FLAT : 0) | (CFG & KS_N2N ? FLAG_NAN_TO_NUM : 0))
                                : a.pw.flags;
     const int H = a.H, W = a.W;
+    const int n_groups = a.n_frames / NF;
 
     float* sconst = (float*)(smem + B::bar_off + 2 * KS_NSTAGE * sizeof(uint64_t));      // lo, hi, thr (double)
     if (threadIdx.x == 0) {
@@ -131,19 +171,21 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     if (warp == KS_CW) {
         // ------------------------------------------------------------------ producer
         if (lane != 0) return;
-        const uint32_t tx_bytes = (uint32_t)(B::raw_bytes + (has_dark ? B::map_bytes : 0) + (has_flat ? B::map_bytes : 0));
+        const uint32_t tx_bytes = (uint32_t)(NF * B::raw_bytes + (has_dark ? B::map_bytes : 0) + (has_flat ? B::map_bytes : 0));
         uint32_t g = 0;
         for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-            const UnitGeom u = ks_unit<KS_R>(unit, strips, segs, seg_rows, H, a.n_frames);
+            const UnitGeom u = ks_unit<KS_R, NF>(unit, strips, seg_rows, H, n_groups);
             for (int k = 0; k < u.nchunk; ++k, ++g) {
                 const int stage = g % KS_NSTAGE;
                 mbar_wait(&empty[stage], ((g / KS_NSTAGE) & 1) ^ 1);
                 uint8_t* base = smem + (size_t)stage * B::stage_bytes;
                 const int y = u.yl0 + k * KS_R;
                 mbar_expect_tx(&full[stage], tx_bytes);
-                tma_load_3d(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame);
-                if (has_dark) tma_load_2d(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
-                if (has_flat) tma_load_2d(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
+#pragma unroll
+                for (int f = 0; f < NF; ++f)
+                    tma_load_3d(base + f * B::raw_bytes, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame + f);
+                if (has_dark) tma_load_2d(base + NF * B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
+                if (has_flat) tma_load_2d(base + NF * B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
             }
         }
         return;
@@ -156,10 +198,11 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     pred.lo = sconst[0]; pred.hi = sconst[1]; pred.thr = *(const double*)(sconst + 2);
     if (CFG >= 0) pred.cond = (CFG & KS_LT) ? COND_LT : COND_GT;
     const int lc = warp * KS_SW - 1 + lane;            // strip-local column of this lane: -1 .. 120
+    const ptrdiff_t frame_px = (ptrdiff_t)H * W;
     uint32_t g = 0;
 
     for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const UnitGeom u = ks_unit<KS_R>(unit, strips, segs, seg_rows, H, a.n_frames);
+        const UnitGeom u = ks_unit<KS_R, NF>(unit, strips, seg_rows, H, n_groups);
         const int gc = u.tx0 + lc;
         const int rc = reflect_index(gc, W);             // scipy 'reflect' in x: halo / outside lanes read the mirrored column
         int mcol = rc - (u.tx0 - KS_MAPX);
@@ -168,55 +211,79 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
         rcol = rcol < 0 ? 0 : (rcol > B::BOXW - 1 ? B::BOXW - 1 : rcol);
         const bool valid = lane >= 1 && lane <= KS_SW && gc < W;
         const int i_first = u.ys == 0 ? 1 : 2;           // first input row index whose step emits an output row
-        const ptrdiff_t o0 = ((ptrdiff_t)u.frame * H + u.yl0 - 1) * W + gc;          // row (yl0 + i - 1) at step i
+        const ptrdiff_t o0 = ((ptrdiff_t)u.frame * H + u.yl0 - 1) * W + gc;          // row (yl0 + i - 1) at step i, first frame
         OutT* outp = (OutT*)a.out + o0;
         uint8_t* maskp = has_mask ? a.mask + o0 : nullptr;
 
-        Sorted3<float> s0, s1;
-        float c1;
+        Sorted3<float> s0[NF], s1[NF];
+        float c1[NF];
         int i = 0;
 
-        auto pixel = [&](const uint8_t* base, int j) -> float {
-            RawT rv = ((const RawT*)base)[j * B::BOXW + rcol];
+        auto maps = [&](const uint8_t* base, int j, RowMaps& m) {
+            m.d = has_dark ? ((const float*)(base + NF * B::raw_bytes))[j * KS_MAPW + mcol] : 0.0f;
+            m.f = has_flat ? ((const float*)(base + NF * B::raw_bytes + B::map_bytes))[j * KS_MAPW + mcol] : 0.0f;
+            if (FASTDIV) {
+                m.dd = (double)m.d;
+                m.fd = (double)m.f;
+                m.y = rcp_f32range(m.fd);
+            }
+        };
+        auto pixel = [&](const uint8_t* base, int j, int f, const RowMaps& m) -> float {
+            RawT rv = ((const RawT*)(base + f * B::raw_bytes))[j * B::BOXW + rcol];
             if (sizeof(RawT) == 2 && swap) rv = (RawT)__byte_perm((unsigned)rv, 0u, 0x0001);
-            const float d = has_dark ? ((const float*)(base + B::raw_bytes))[j * KS_MAPW + mcol] : 0.0f;
-            const float f = has_flat ? ((const float*)(base + B::raw_bytes + B::map_bytes))[j * KS_MAPW + mcol] : 0.0f;
             double rd; float ra;
             StreamRaw<RawT>::ld(rv, rd, ra);
+            float x;
             bool ok;
-            float x = (CFG >= 0 && (CFG & KS_NZ)) ? pointwise_fast_nz(flags, rd, ra, d, f, ok) : pointwise_fast(flags, rd, ra, d, f, ok);
-            if (check) { if (!ok) x = pointwise<float>(pw, rd, d, 0.0f, f); }
+            if (FASTDIV) {
+                x = (float)ddiv_rcp(dsub(rd, m.dd), m.fd, m.y);
+                if (flags & FLAG_NAN_TO_NUM) x = fminf(fmaxf(x, -FLT_MAX), FLT_MAX);
+                if (check) ok = (fabsf(m.d) + fabsf(m.f) + ra) <= FLT_MAX;
+            } else {
+                x = (CFG >= 0 && (CFG & KS_NZ)) ? pointwise_fast_nz(flags, rd, ra, m.d, m.f, ok) : pointwise_fast(flags, rd, ra, m.d, m.f, ok);
+            }
+            if (check) { if (!ok) x = pointwise<float>(pw, rd, m.d, 0.0f, m.f); }
             return x;
         };
-        auto emit = [&](const Sorted3<float>& t2, bool on) {
+        auto triple = [&](float x) -> Sorted3<float> {
+            const float l = __shfl_up_sync(0xffffffffu, x, 1);
+            const float r = __shfl_down_sync(0xffffffffu, x, 1);
+            return sort3(l, x, r);
+        };
+        // slow path: one row of frame f, any row (first rows of a unit, short last chunk, guard-band redo)
+        auto emit = [&](int f, const Sorted3<float>& t2, bool on) {
+            OutT* op = outp + f * frame_px;
             if (nomed) {
-                if (on) *outp = ks_out<OutT>(c1);
+                if (on) *op = ks_out<OutT>(c1[f]);
                 return;
             }
-            const float med = median9(s0, s1, t2);
+            const float med = median9(s0[f], s1[f], t2);
             bool rep;
-            const bool sure = predicate_certain(c1, med, pred, rep);
+            const bool sure = predicate_certain(c1[f], med, pred, rep);
             if (on) {
-                *outp = ks_out<OutT>(rep ? med : c1);
+                *op = ks_out<OutT>(rep ? med : c1[f]);
                 if (has_mask) *maskp = rep ? 1 : 0;
             }
             // ~1e-5 of the pixels fall inside the guard band of the float32 test: those lanes evaluate the reference's
             // float64 expression out of line and overwrite their result (one warp-uniform branch in the common case)
             if (__any_sync(0xffffffffu, !sure)) {
                 if (!sure && on) {
-                    const bool r2 = ks_exact(c1, med, pred.thr, pred.cond);
-                    *outp = ks_out<OutT>(r2 ? med : c1);
+                    const bool r2 = ks_exact(c1[f], med, pred.thr, pred.cond);
+                    *op = ks_out<OutT>(r2 ? med : c1[f]);
                     if (has_mask) *maskp = r2 ? 1 : 0;
                 }
             }
         };
         auto row = [&](const uint8_t* base, int j) {
-            const float x = pixel(base, j);
-            const float l = __shfl_up_sync(0xffffffffu, x, 1);
-            const float r = __shfl_down_sync(0xffffffffu, x, 1);
-            const Sorted3<float> t2 = sort3(l, x, r);
-            emit(t2, valid && i >= i_first);
-            s0 = s1; s1 = t2; c1 = x;
+            RowMaps m;
+            maps(base, j, m);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const float x = pixel(base, j, f, m);
+                const Sorted3<float> t2 = triple(x);
+                emit(f, t2, valid && i >= i_first);
+                s0[f] = s1[f]; s1[f] = t2; c1[f] = x;
+            }
             outp += W;
             if (has_mask) maskp += W;
             ++i;
@@ -228,46 +295,63 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
             const uint8_t* base = smem + (size_t)stage * B::stage_bytes;
             if (k == 0) {
                 // vertical 'reflect' at the top (and a defined s0/s1 elsewhere): the first row's triple is used twice
-                const float x = pixel(base, 0);
-                const float l = __shfl_up_sync(0xffffffffu, x, 1);
-                const float r = __shfl_down_sync(0xffffffffu, x, 1);
-                s1 = sort3(l, x, r);
-                s0 = s1;
-                c1 = x;
+                RowMaps m;
+                maps(base, 0, m);
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    const float x = pixel(base, 0, f, m);
+                    s1[f] = triple(x);
+                    s0[f] = s1[f];
+                    c1[f] = x;
+                }
             }
             const int rows = u.n_in - k * KS_R;
             if (k > 0 && rows >= KS_R) {
                 // steady state: every row emits; the store is unconditional (lanes without an output pixel write to
                 // a private scratch slot) and the guard-band test is only accumulated — if any lane of the warp hit the
                 // band in this chunk (rare), the chunk is redone below with the exact predicate.
-                const Sorted3<float> k0 = s0, k1 = s1;
-                const float kc = c1;
-                OutT* op = valid ? outp : (OutT*)a.dump + (size_t)blockIdx.x * KS_THREADS + threadIdx.x;
+                Sorted3<float> k0[NF], k1[NF];
+                float kc[NF];
+                OutT* op[NF];
+#pragma unroll
+                for (int f = 0; f < NF; ++f) {
+                    k0[f] = s0[f]; k1[f] = s1[f]; kc[f] = c1[f];
+                    op[f] = valid ? outp + f * frame_px
+                                  : (OutT*)a.dump + ((size_t)f * gridDim.x + blockIdx.x) * KS_THREADS + threadIdx.x;
+                }
                 uint8_t* mp = has_mask ? (valid ? maskp : (uint8_t*)a.dump + (size_t)(gridDim.x + blockIdx.x) * KS_THREADS * sizeof(OutT) + threadIdx.x) : nullptr;
-                const int ostride = valid ? W : 0;
+                const int ostride = valid ? W : 0;       // element index j * ostride stays below 2^31 (R * 32767)
                 bool unsure = false;
 #pragma unroll
-                for (int j = 0; j < KS_R; ++j) {
-                    const float x = pixel(base, j);
-                    if (nomed) {
-                        *op = ks_out<OutT>(c1);
-                        op += ostride;
-                        c1 = x;
-                        continue;
+                for (int j = 0; j < KS_R; j += 2) {
+                    RowMaps ma, mb;
+                    maps(base, j, ma);
+                    maps(base, j + 1, mb);
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) {
+                        const float xa = pixel(base, j, f, ma);
+                        const float xb = pixel(base, j + 1, f, mb);
+                        if (nomed) {
+                            op[f][j * ostride] = ks_out<OutT>(c1[f]);
+                            op[f][(j + 1) * ostride] = ks_out<OutT>(xa);
+                            c1[f] = xb;
+                            continue;
+                        }
+                        const Sorted3<float> ta = triple(xa), tb = triple(xb);
+                        float m1, m2;
+                        median9_pair(s0[f], s1[f], ta, tb, m1, m2);
+                        bool r1, r2;
+                        unsure |= !predicate_certain(c1[f], m1, pred, r1);
+                        unsure |= !predicate_certain(xa, m2, pred, r2);
+                        op[f][j * ostride] = ks_out<OutT>(r1 ? m1 : c1[f]);
+                        op[f][(j + 1) * ostride] = ks_out<OutT>(r2 ? m2 : xa);
+                        if (has_mask) { mp[j * ostride] = r1 ? 1 : 0; mp[(j + 1) * ostride] = r2 ? 1 : 0; }
+                        s0[f] = ta; s1[f] = tb; c1[f] = xb;
                     }
-                    const float l = __shfl_up_sync(0xffffffffu, x, 1);
-                    const float r = __shfl_down_sync(0xffffffffu, x, 1);
-                    const Sorted3<float> t2 = sort3(l, x, r);
-                    const float med = median9(s0, s1, t2);
-                    bool rep;
-                    unsure |= !predicate_certain(c1, med, pred, rep);
-                    *op = ks_out<OutT>(rep ? med : c1);
-                    if (has_mask) { *mp = rep ? 1 : 0; mp += ostride; }
-                    op += ostride;
-                    s0 = s1; s1 = t2; c1 = x;
                 }
                 if (__any_sync(0xffffffffu, unsure)) {
-                    s0 = k0; s1 = k1; c1 = kc;
+#pragma unroll
+                    for (int f = 0; f < NF; ++f) { s0[f] = k0[f]; s1[f] = k1[f]; c1[f] = kc[f]; }
                     for (int j = 0; j < KS_R; ++j) row(base, j);
                 } else {
                     outp += (size_t)KS_R * W;
@@ -283,8 +367,11 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
         }
         if (u.ye == H) {
             // vertical 'reflect' at the bottom: output row H-1 sees (H-2, H-1, H-1)
-            const Sorted3<float> t2 = s1;
-            emit(t2, valid);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                const Sorted3<float> t2 = s1[f];
+                emit(f, t2, valid);
+            }
         }
     }
 }
@@ -306,10 +393,35 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
     return tensor_map_encoder() != nullptr;
 }
 
+typedef void (*ks_kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int);
+
+// cudaFuncSetAttribute is per device and the occupancy answer too: cache both per (device, kernel)
+static int ks_blocks_per_sm(ks_kern_t kern, size_t smem, cudaError_t* err) {
+    constexpr int MAXDEV = 64, MAXK = 64;
+    static struct { ks_kern_t k; int per_sm[MAXDEV]; } table[MAXK];
+    static int used = 0;
+    static std::mutex mu;
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    int slot = -1;
+    for (int s = 0; s < used; ++s) if (table[s].k == kern) { slot = s; break; }
+    if (slot < 0 && used < MAXK) { slot = used++; table[slot].k = kern; for (int d = 0; d < MAXDEV; ++d) table[slot].per_sm[d] = 0; }
+    if (slot >= 0 && dev < MAXDEV && table[slot].per_sm[dev]) return table[slot].per_sm[dev];
+    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return 0;
+    int n = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, KS_THREADS, smem);
+    if (n < 1) n = 1;
+    if (slot >= 0 && dev < MAXDEV) table[slot].per_sm[dev] = n;
+    return n;
+}
+
 template <typename RawT, typename OutT, typename C>
 static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
     using B = StreamBox<RawT, C>;
-    constexpr int KS_R = C::R;
+    constexpr int KS_R = C::R, NF = C::NF;
     K1Args a = a_in;
     // pick the instantiation: the hot configurations are fully specialised, the rest read their flags at run time
     const bool check = !a.maps_finite || sizeof(RawT) == 4;
@@ -317,25 +429,30 @@ static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, 
     const bool chain = a.ksize == 3 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
                        a.pred.cond == COND_GT;
     const bool plain = a.ksize == 3 && !(f & (FLAG_DARK | FLAG_FLAT | FLAG_NAN_TO_NUM)) && a.mask && a.pred.cond == COND_GT;
-    void (*kern)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int, int);
-    int slot;
+    ks_kern_t kern = nullptr;
     // threshold <= 0: dark + flat only (nan_to_num is not applied then, CameraCalibration.py:556-561)
     const bool pw_only = a.ksize == 0 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && !a.raw_swap && !check;
     if (chain || pw_only) a.flat = a.flat_nz;          // zero-free copy: "divide where flat != 0" becomes an unconditional division
-    if (pw_only) {
-        kern = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_NOMED, C>
-                                                       : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_NOMED, C>;
-        slot = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? 7 : 8;
-    } else if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
-        kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP, C>
-                             : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP, C>;
-        slot = a.no_overflow ? 5 : 6;
-    } else if (a.raw_swap) { kern = k1_stream_kernel<RawT, OutT, -1, C>; slot = 4; if (chain) a.flat = a_in.flat; }
-    else if (chain && !check && a.no_overflow) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ, C>; slot = 0; }
-    else if (chain && !check) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ, C>; slot = 1; }
-    else if (chain) { kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK, C>; slot = 2; }
-    else if (plain) { kern = k1_stream_kernel<RawT, OutT, KS_MASK, C>; slot = 3; }
-    else { kern = k1_stream_kernel<RawT, OutT, -1, C>; slot = 4; }
+    if constexpr (NF > 1) {
+        // frame-pair units: the chain configurations only (launch_stream_t sends nothing else here)
+        if (!chain || a.raw_swap || a.n_frames % NF) return cudaErrorInvalidValue;
+        if (!check && a.no_overflow) kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ, C>;
+        else if (!check) kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ, C>;
+        else kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK, C>;
+    } else {
+        if (pw_only) {
+            kern = (f & FLAG_NAN_TO_NUM) && !a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_NOMED, C>
+                                                           : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_NOMED, C>;
+        } else if (a.raw_swap && chain && !check && sizeof(RawT) == 2) {
+            kern = a.no_overflow ? k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ | KS_SWAP, C>
+                                 : k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_SWAP, C>;
+        } else if (a.raw_swap) { kern = k1_stream_kernel<RawT, OutT, -1, C>; if (chain) a.flat = a_in.flat; }
+        else if (chain && !check && a.no_overflow) kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_NZ, C>;
+        else if (chain && !check) kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ, C>;
+        else if (chain) kern = k1_stream_kernel<RawT, OutT, KS_DARK | KS_FLAT | KS_N2N | KS_NZ | KS_CHECK, C>;
+        else if (plain) kern = k1_stream_kernel<RawT, OutT, KS_MASK, C>;
+        else kern = k1_stream_kernel<RawT, OutT, -1, C>;
+    }
 
     CUtensorMap tr, td, tf;
     if (!make_tensor_map(&tr, rdt, sizeof(RawT), a.raw, a.W, a.H, a.n_frames, B::BOXW, KS_R)) return cudaErrorInvalidValue;
@@ -343,16 +460,12 @@ static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, 
         return cudaErrorInvalidValue;
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
-    static int per_sm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (!per_sm[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
-        if (e != cudaSuccess) return e;
-        int n = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, KS_THREADS, B::total);
-        per_sm[slot] = n < 1 ? 1 : n;
-    }
+    cudaError_t e = cudaSuccess;
+    const int per_sm = ks_blocks_per_sm(kern, B::total, &e);
+    if (e != cudaSuccess) return e;
     const int strips = (a.W + KS_TW - 1) / KS_TW;
-    const long long slots = (long long)sm_count * per_sm[slot];
+    const int n_groups = a.n_frames / NF;
+    const long long slots = (long long)sm_count * per_sm;
     if (seg_rows <= 0) {
         // all units cost the same: pick the segment height whose unit count fills whole waves of the resident CTAs best,
         // counting the two re-read halo rows per segment against it.  (Searching beyond 8 waves finds better fills on
@@ -360,11 +473,11 @@ static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, 
         // the pipeline and runs its first chunk row by row.)
         double best = -1.0;
         for (int waves = 1; waves <= 8; ++waves) {
-            long long segs_try = slots * waves / ((long long)strips * a.n_frames);
+            long long segs_try = slots * waves / ((long long)strips * n_groups);
             if (segs_try < 1) continue;
             int rows = (int)((a.H + segs_try - 1) / segs_try);
             if (rows < 2 * KS_R) rows = 2 * KS_R;
-            const long long units = (long long)strips * ((a.H + rows - 1) / rows) * a.n_frames;
+            const long long units = (long long)strips * ((a.H + rows - 1) / rows) * n_groups;
             const double util = (double)units / (double)(((units + slots - 1) / slots) * slots) * rows / (rows + 2.0);
             if (util > best) { best = util; seg_rows = rows; }
         }
@@ -372,18 +485,39 @@ static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, 
     }
     if (seg_rows < 4) seg_rows = 4;
     const int segs = (a.H + seg_rows - 1) / seg_rows;
-    const long long total = (long long)strips * segs * a.n_frames;
+    const long long total = (long long)strips * segs * n_groups;
     if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
     long long grid = slots;
     if (grid > total) grid = total;
-    kern<<<(unsigned)grid, KS_THREADS, B::total, st>>>(tr, td, tf, a, strips, segs, seg_rows, (int)total);
+    kern<<<(unsigned)grid, KS_THREADS, B::total, st>>>(tr, td, tf, a, strips, seg_rows, (int)total);
     return cudaGetLastError();
 }
 
 template <typename RawT, typename OutT>
 static cudaError_t launch_stream_t(const K1Args& a, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
-    // the wide shape pays with float32 output and a few frames per launch (see KsShape)
-    if (sizeof(OutT) == 4 && a.n_frames >= 4) return launch_stream_c<RawT, OutT, KsWide>(a, rdt, sm_count, seg_rows, st);
+    if constexpr (sizeof(OutT) == 4) {
+        const int f = a.pw.flags;
+        const bool chain = a.ksize == 3 && a.dark && a.flat && a.flat_nz && (f & FLAG_DARK) && (f & FLAG_FLAT) && (f & FLAG_NAN_TO_NUM) && !a.mask &&
+                           a.pred.cond == COND_GT && !a.raw_swap;
+        // batches of the chain configuration: two frames per work unit share the dark / flat half of the arithmetic;
+        // an odd last frame goes through the one-frame kernel
+#ifndef KS_NO_PAIR
+        if (chain && a.n_frames >= 4) {
+            const int even = a.n_frames & ~1;
+            K1Args b = a;
+            b.n_frames = even;
+            cudaError_t e = launch_stream_c<RawT, OutT, KsPair>(b, rdt, sm_count, seg_rows, st);
+            if (e != cudaSuccess || even == a.n_frames) return e;
+            b = a;
+            b.n_frames = 1;
+            b.raw = (const char*)a.raw + (size_t)even * a.H * a.W * sizeof(RawT);
+            b.out = (char*)a.out + (size_t)even * a.H * a.W * sizeof(OutT);
+            return launch_stream_c<RawT, OutT, KsNarrow>(b, rdt, sm_count, seg_rows, st);
+        }
+#endif
+        // the wide shape pays with float32 output and a few frames per launch (see KsShape)
+        if (a.n_frames >= 4) return launch_stream_c<RawT, OutT, KsWide>(a, rdt, sm_count, seg_rows, st);
+    }
     return launch_stream_c<RawT, OutT, KsNarrow>(a, rdt, sm_count, seg_rows, st);
 }
 

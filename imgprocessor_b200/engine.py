@@ -86,6 +86,13 @@ class Engine(object):
         _lib.check(self.lib.imgcorr_profile_read(self._h, buf))
         return tuple(buf)
 
+    def selftest_division(self, numerators_per_divisor=16, seed=1):
+        """(mismatches, worst seed error) of the shortened float64 division sequence against IEEE division, run on the
+        device for every float32 significand pattern of the divisor (imgcorr_selftest_division)"""
+        buf = (ctypes.c_double * 2)()
+        _lib.check(self.lib.imgcorr_selftest_division(self._h, int(numerators_per_divisor), int(seed), buf))
+        return int(buf[0]), float(buf[1])
+
     def _stream(self):
         return ctypes.c_void_p(torch().cuda.current_stream(self.device).cuda_stream)
 

@@ -62,7 +62,7 @@ enum {
 
 /* imgcorr_set_option keys */
 enum {
-    IMGCORR_OPT_K1_VARIANT = 1, /* 0 auto, 1 generic tiles, 2 TMA-staged tiles, 3 / 4 TMA streaming pipeline v1 (3x3 and 5x5) / v2 (3x3, two columns per lane) (2-4 fail if not eligible) */
+    IMGCORR_OPT_K1_VARIANT = 1, /* 0 auto, 1 generic tiles, 2 TMA-staged tiles, 3 TMA streaming pipeline (3x3 and 5x5) (2-3 fail if not eligible) */
     IMGCORR_OPT_K2_VARIANT = 2, /* 0 auto, 1 gathers through L1/L2, 2 shared-memory staged tiles (float32 / uint16 / uint8 sources; fails if not eligible) */
     IMGCORR_OPT_HOST_SLOTS = 3, /* depth of the pinned / device staging ring of the *_host calls (default 4) */
     IMGCORR_OPT_K1_SEG_ROWS = 4, /* rows per work unit of the streaming K1 kernel (0 = default) */
@@ -186,6 +186,15 @@ IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* ctx, const void* src_dev, int sr
  * MaskedMovingAverage (absent from the reference tree: that ingredient's parity is unpinned, see oracle/ste.py). */
 IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
                         uint8_t* mask_dev, const double nlf[3], double n_std, void* stream);
+
+/* ---- self-test ---------------------------------------------------------------------------------------
+ * K1 and K4 divide in float64 with a shortened Newton sequence (MUFU.RCP64H seed, one refinement, residual correction:
+ * csrc/imgcorr_core.cuh rcp_f32range / ddiv_rcp) that is exact only because the divisors are float32-derived or small
+ * integers.  This runs the sequence on the device for every float32 significand pattern of the divisor (both signs,
+ * exponents cycling over the float32 range), `numerators_per_divisor` numerators each, against IEEE division:
+ *   out[0] = quotients that differ from IEEE a / b (must be 0), out[1] = largest |1 - b * seed| seen (seed quality).
+ * Synchronous. */
+IMGCORR_API int imgcorr_selftest_division(imgcorr_ctx* ctx, int numerators_per_divisor, unsigned long long seed, double out[2]);
 
 /* page-locked host memory for the *_host entry points */
 IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr);
