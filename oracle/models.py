@@ -182,26 +182,37 @@ def bilinear_weights_f32(fx, fy):
     return (one - ty) * (one - tx), (one - ty) * tx, ty * (one - tx), ty * tx
 
 
-def _gather(src, ix, iy, border):
-    H, W = src.shape
+def _gather(src, ix, iy, border, row0=0, height=None):
+    """src holds rows [row0, row0 + src.shape[0]) of a frame of `height` rows (default: the whole frame)"""
+    hb, W = src.shape
+    H = hb if height is None else height
     ok = (ix >= 0) & (ix < W) & (iy >= 0) & (iy < H)
-    v = src[np.clip(iy, 0, H - 1), np.clip(ix, 0, W - 1)]
+    local = iy - row0
+    assert not (ok & ((local < 0) | (local >= hb))).any(), 'remap reads a source row outside the supplied band'
+    v = src[np.clip(local, 0, hb - 1), np.clip(ix, 0, W - 1)]
     return np.where(ok, v, border)
 
 
-def remap_model(src, mapx, mapy, border_value=0):
+def remap_model(src, mapx, mapy, border_value=0, src_row0=0, src_height=None):
     """Model of cv2.remap(src, mapx, mapy, INTER_LINEAR, BORDER_CONSTANT,
     border_value) for 2-D uint8 / uint16 / float32 / float64 images.
     * float32, uint16: float32 accumulate ((v00 w00 + v01 w01) + v10 w10) + v11 w11,
       every product and sum rounded separately (no FMA); uint16 then rounds
       half-even and saturates.
     * float64: same order in float64 with the float32 weights promoted.
-    * uint8: int16 weights (w * 2**15), int32 accumulate, (acc + 2**14) >> 15."""
+    * uint8: int16 weights (w * 2**15), int32 accumulate, (acc + 2**14) >> 15.
+    ``src`` may be a band of rows [src_row0, src_row0 + len(src)) of a frame of ``src_height`` rows (the maps stay
+    in full-frame coordinates; every in-frame row the maps touch must lie inside the band)."""
     src = np.asarray(src)
     assert src.ndim == 2
     ix, iy, fx, fy = fixed_point_coords(mapx, mapy)
     w00, w01, w10, w11 = bilinear_weights_f32(fx, fy)
     H, W = src.shape
+    if src_height is not None:
+        H = src_height
+
+    def gat(s, jx, jy, b):                          # band-aware gather
+        return _gather(s, jx, jy, b, src_row0, H)
     # a 2x2 window entirely outside the image yields the border value itself (not a blend of it)
     outside = (ix >= W) | (ix + 1 < 0) | (iy >= H) | (iy + 1 < 0)
     if src.dtype == np.uint8:
@@ -209,8 +220,8 @@ def remap_model(src, mapx, mapy, border_value=0):
         iw = [np.rint(w.astype(np.float64) * sc).astype(np.int64) for w in (w00, w01, w10, w11)]
         s = src.astype(np.int64)
         b = int(np.clip(np.rint(border_value), 0, 255))
-        acc = (_gather(s, ix, iy, b) * iw[0] + _gather(s, ix + 1, iy, b) * iw[1]
-               + _gather(s, ix, iy + 1, b) * iw[2] + _gather(s, ix + 1, iy + 1, b) * iw[3])
+        acc = (gat(s, ix, iy, b) * iw[0] + gat(s, ix + 1, iy, b) * iw[1]
+               + gat(s, ix, iy + 1, b) * iw[2] + gat(s, ix + 1, iy + 1, b) * iw[3])
         r = (acc + (1 << (INTER_REMAP_COEF_BITS - 1))) >> INTER_REMAP_COEF_BITS
         return np.where(outside, b, np.clip(r, 0, 255)).astype(np.uint8)
     if src.dtype == np.float64:
@@ -225,8 +236,8 @@ def remap_model(src, mapx, mapy, border_value=0):
     s = src.astype(acc_t)
     w00, w01, w10, w11 = (w.astype(acc_t) for w in (w00, w01, w10, w11))
     with np.errstate(over='ignore', invalid='ignore'):
-        r = ((_gather(s, ix, iy, b) * w00 + _gather(s, ix + 1, iy, b) * w01)
-             + _gather(s, ix, iy + 1, b) * w10) + _gather(s, ix + 1, iy + 1, b) * w11
+        r = ((gat(s, ix, iy, b) * w00 + gat(s, ix + 1, iy, b) * w01)
+             + gat(s, ix, iy + 1, b) * w10) + gat(s, ix + 1, iy + 1, b) * w11
     r = np.where(outside, b, r)
     if src.dtype == np.uint16:
         return np.clip(np.rint(r), 0, 65535).astype(np.uint16)

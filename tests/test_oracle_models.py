@@ -93,3 +93,26 @@ def test_full_size_chain_smoke():
     got, mask = models.correct_chain_f32(raw, dark, flat, 0.1, 3, (K, d, P))
     assert 0.001 < mask.mean() < 0.05
     assert np.abs(got - ref).max() / 4095.0 < 1e-5
+
+
+def test_band_chain_equals_full_chain():
+    """oracle/bands.py (what bench.py and the full-size GPU tests check against) reproduces the full-frame oracle chain
+    row for row, for 3x3 and 5x5, at frame edges and interior bands, through a strong lens"""
+    import cv2
+    from imgprocessor_b200 import synth
+    from oracle import bands
+    H, W = 300, 416
+    raw = synth.scene(H, W, 3, np.uint16)
+    dark, flat = synth.dark_map(H, W), synth.flat_map(H, W, p_zero=1e-3)
+    for lens in (synth.lens_moderate(H, W), synth.lens_strong(H, W)):
+        K, d = synth.camera_matrix(lens), synth.dist_coeffs(lens)
+        P, _ = cv2.getOptimalNewCameraMatrix(K, d, (W, H), 1, (W, H))
+        mapx, mapy = cv2.initUndistortRectifyMap(K, d, None, P, (W, H), cv2.CV_32FC1)
+        for size in (3, 5):
+            full, _ = models.correct_chain_f32(raw, dark, flat, 0.1, size, mapxy=(mapx, mapy))
+            k1, _ = models.median_threshold_model(models.pointwise_model(raw, dark, flat, True), 0.1, size)
+            for r0, r1 in bands.default_bands(H, 40) + [(7, 19), (290, 300)]:
+                assert np.array_equal(bands.chain_band(raw, dark, flat, mapx, mapy, r0, r1, 0.1, size), full[r0:r1])
+                assert np.array_equal(bands.k1_band(raw, dark, flat, r0, r1, 0.1, size), k1[r0:r1])
+    full, _ = models.correct_chain_f32(raw, dark, flat, 0, 3, mapxy=(mapx, mapy))
+    assert np.array_equal(bands.chain_band(raw, dark, flat, mapx, mapy, 100, 140, 0, 3), full[100:140], equal_nan=True)
