@@ -266,12 +266,15 @@ class Parity(object):
 
 
 def event_times_us(fn, iters, warm=3):
-    """median / min duration in us of fn(i), each call bracketed by CUDA events on the current stream"""
+    """median / min duration in us of fn(i), each call bracketed by CUDA events on the current stream.  A ~20 ms spin
+    kernel is queued first so that the calls pile up behind it: the events then time the GPU, not the Python call rate
+    (a one-frame call costs ~50 us of host time, more than the kernels of a small frame)."""
     import torch
     for i in range(warm):
         fn(i)
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    torch.cuda._sleep(40000000)
     ev[0].record()
     for i in range(iters):
         fn(i)

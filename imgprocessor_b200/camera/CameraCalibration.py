@@ -47,13 +47,14 @@ def _getFromDate(entries, date):
 
 
 def _map_token(kind, arr):
-    """identity of a calibration map for the engine's upload cache: the array object plus a fingerprint of ~4000 strided
-    samples, so that an array modified in place between two calls is uploaded again (the reference reads it every call)"""
+    """identity of a calibration map for the engine's upload cache: shape, dtype and a fingerprint of EVERY byte of the
+    array (imgcorr_host_fingerprint: a few host threads, ~1 ms for a 4096x3000 float32 map), so that an array modified in
+    place between two calls — a patched hot pixel is enough — is uploaded again.  The reference reads the array on every
+    call (camera/CameraCalibration.py:500-502, 521-526); `id()` is not part of the key (ids are recycled)."""
     if not isinstance(arr, np.ndarray):
         return None
-    flat = arr.reshape(-1)
-    step = max(1, flat.size // 4096)
-    return (kind, id(arr), arr.shape, arr.dtype.str, hash(flat[::step].tobytes()))
+    a = arr if arr.flags.c_contiguous else np.ascontiguousarray(arr)
+    return (kind, arr.shape, arr.dtype.str, _engine.host_fingerprint(a))
 
 
 class _BoundedNLF(object):

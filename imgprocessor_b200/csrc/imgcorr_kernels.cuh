@@ -54,7 +54,10 @@ struct K2Args {
     double border;
     LensConst lens;
     const double* lens_dev;  // device copy of the lens constants (see LensPack), loaded once per thread into registers
+    int geometry;            // tiled variant: staged-box geometry (k2_pick_geometry), 0 = 80x32 box for 64x16 tiles
+    const float4* wtab;      // device copy of OpenCV's 32 x 32 bilinear weight table [fy][fx] = (w00, w01, w10, w11)
 };
+int k2_pick_geometry(const LensConst& lens, int H, int W, int x0, int y0, int ow, int oh);
 
 // order of the doubles in K2Args::lens_dev
 enum LensPack : int { LP_K1, LP_K2, LP_K3, LP_P1, LP_P2, LP_P1X2, LP_P2X2, LP_FX, LP_FY, LP_CX, LP_CY, LP_IR0, LP_IR2, LP_IR4, LP_IR5, LP_PAD, LP_COUNT };

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 
 namespace imgcorr {
 
@@ -49,6 +50,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// tiled bulk tensor store shared -> global (bulk async-group completion); parts of the box outside the tensor are
+// not written.  Sequence: write the tile with ordinary stores, fence_proxy_async_smem() in every writing thread,
+// barrier, one thread issues the store + commit, and waits for `.read` before the tile is overwritten.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int x, int y, int z) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tm), "r"(smem_u32(src)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ---- host ---------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -66,6 +78,32 @@ inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
             fn = (PFN_tensorMapEncodeTiled)p;
     }
     return fn;
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the occupancy answer are per DEVICE: a process may hold contexts on
+// several devices (imgcorr_ctx_create(device, ...)), so both are cached per (device, kernel) under a lock.  Returns the
+// resident CTAs per SM (>= 1), 0 with *err set on failure.
+inline int blocks_per_sm_cached(const void* kern, int threads, size_t smem, cudaError_t* err) {
+    constexpr int MAXDEV = 64, MAXK = 256;
+    struct Entry { const void* k; int per_sm[MAXDEV]; };
+    static Entry table[MAXK];
+    static int used = 0;
+    static std::mutex mu;
+    int dev = 0;
+    *err = cudaGetDevice(&dev);
+    if (*err != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    int slot = -1;
+    for (int s = 0; s < used; ++s) if (table[s].k == kern) { slot = s; break; }
+    if (slot < 0 && used < MAXK) { slot = used++; table[slot].k = kern; for (int d = 0; d < MAXDEV; ++d) table[slot].per_sm[d] = 0; }
+    if (slot >= 0 && dev < MAXDEV && table[slot].per_sm[dev]) return table[slot].per_sm[dev];
+    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (*err != cudaSuccess) return 0;
+    int n = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+    if (n < 1) n = 1;
+    if (slot >= 0 && dev < MAXDEV) table[slot].per_sm[dev] = n;
+    return n;
 }
 
 // dense row-major [N][H][W] (N == 0: [H][W], rank 2) of `esz`-byte elements, box = boxw x boxh (x 1)

@@ -397,15 +397,9 @@ static cudaError_t launch_tma_t(const K1Args& a, CUtensorMapDataType rdt, int sm
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K1_BOXW, boxh) && a.flat)
         return cudaErrorInvalidValue;
     auto kern = k1_tma_kernel<RawT, OutT, KS, TH, NSTAGE>;
-    static bool attr_set = false;
-    static int per_sm = 1;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total);
-        if (e != cudaSuccess) return e;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, K1_THREADS, S::total);
-        if (per_sm < 1) per_sm = 1;
-        attr_set = true;
-    }
+    cudaError_t e = cudaSuccess;
+    const int per_sm = blocks_per_sm_cached((const void*)kern, K1_THREADS, S::total, &e);     // per (device, kernel)
+    if (e != cudaSuccess) return e;
     const int tiles_x = (a.W + K1_TW - 1) / K1_TW, tiles_y = (a.H + TH - 1) / TH;
     const long long total = (long long)tiles_x * tiles_y * a.n_frames;
     long long grid = (long long)sm_count * per_sm;

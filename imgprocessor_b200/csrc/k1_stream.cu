@@ -21,7 +21,6 @@
 // Same arithmetic as the tile kernels (imgcorr_core.cuh) — results are bit-identical.
 #include "imgcorr_kernels.cuh"
 #include "imgcorr_tma.cuh"
-#include <mutex>
 
 namespace imgcorr {
 
@@ -395,29 +394,6 @@ bool k1_stream_eligible(const K1Args& a, int raw_dtype, int out_dtype) {
 
 typedef void (*ks_kern_t)(const CUtensorMap, const CUtensorMap, const CUtensorMap, K1Args, int, int, int);
 
-// cudaFuncSetAttribute is per device and the occupancy answer too: cache both per (device, kernel)
-static int ks_blocks_per_sm(ks_kern_t kern, size_t smem, cudaError_t* err) {
-    constexpr int MAXDEV = 64, MAXK = 64;
-    static struct { ks_kern_t k; int per_sm[MAXDEV]; } table[MAXK];
-    static int used = 0;
-    static std::mutex mu;
-    int dev = 0;
-    *err = cudaGetDevice(&dev);
-    if (*err != cudaSuccess) return 0;
-    std::lock_guard<std::mutex> lock(mu);
-    int slot = -1;
-    for (int s = 0; s < used; ++s) if (table[s].k == kern) { slot = s; break; }
-    if (slot < 0 && used < MAXK) { slot = used++; table[slot].k = kern; for (int d = 0; d < MAXDEV; ++d) table[slot].per_sm[d] = 0; }
-    if (slot >= 0 && dev < MAXDEV && table[slot].per_sm[dev]) return table[slot].per_sm[dev];
-    *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (*err != cudaSuccess) return 0;
-    int n = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, KS_THREADS, smem);
-    if (n < 1) n = 1;
-    if (slot >= 0 && dev < MAXDEV) table[slot].per_sm[dev] = n;
-    return n;
-}
-
 template <typename RawT, typename OutT, typename C>
 static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count, int seg_rows, cudaStream_t st) {
     using B = StreamBox<RawT, C>;
@@ -461,7 +437,7 @@ static cudaError_t launch_stream_c(const K1Args& a_in, CUtensorMapDataType rdt, 
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, KS_MAPW, KS_R) && a.flat)
         return cudaErrorInvalidValue;
     cudaError_t e = cudaSuccess;
-    const int per_sm = ks_blocks_per_sm(kern, B::total, &e);
+    const int per_sm = blocks_per_sm_cached((const void*)kern, KS_THREADS, B::total, &e);
     if (e != cudaSuccess) return e;
     const int strips = (a.W + KS_TW - 1) / KS_TW;
     const int n_groups = a.n_frames / NF;

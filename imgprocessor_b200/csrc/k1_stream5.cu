@@ -326,16 +326,12 @@ cudaError_t launch5_t(const K1Args& a_in, CUtensorMapDataType rdt, int sm_count,
         return cudaErrorInvalidValue;
     if (!make_tensor_map(&tf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.flat ? (const void*)a.flat : a.raw, a.W, a.H, 0, K5_MAPW, K5_R) && a.flat)
         return cudaErrorInvalidValue;
-    static int per_sm[5] = {0, 0, 0, 0, 0};
-    if (!per_sm[slot]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B::total);
-        if (e != cudaSuccess) return e;
-        int n = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, K5_THREADS, B::total);
-        per_sm[slot] = n < 1 ? 1 : n;
-    }
+    cudaError_t e_attr = cudaSuccess;
+    const int per_sm_k = blocks_per_sm_cached((const void*)kern, K5_THREADS, B::total, &e_attr);     // per (device, kernel)
+    if (e_attr != cudaSuccess) return e_attr;
+    (void)slot;
     const int strips = (a.W + K5_TW - 1) / K5_TW;
-    const long long slots = (long long)sm_count * per_sm[slot];
+    const long long slots = (long long)sm_count * per_sm_k;
     if (seg_rows <= 0) {
         // equal-cost units: pick the segment height whose unit count fills whole waves of the resident CTAs best, counting
         // the four re-read halo rows per segment against it

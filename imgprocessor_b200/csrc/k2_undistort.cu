@@ -30,14 +30,47 @@ constexpr int K2_MINB = K2_MINB_V;
 
 template <typename SrcT> __device__ __forceinline__ SrcT border_cast(double b) { return (SrcT)b; }
 
+// fixed_coord() without the two F2I conversions (the XU pipe is what bounds the coordinate phase of a one-frame launch:
+// 7 conversions per pixel at 16 lanes per clock and SM): cvRound(m * 32) by the magic-number addition
+//   s = m * 32 + 1.5 * 2^23   (one rounding to the integer grid, ties to even = cvRound / cvt.rni)
+// whose bit pattern minus that of the constant is the integer.  The constant's low five bits are zero, so the 1/32-pixel
+// phase is `bits & 31` and the pixel index `(bits - bits(1.5 * 2^23)) >> 5`.  Exact for |m * 32| < 2^22 (every coordinate
+// of a frame up to 32767 pixels a side — larger frames are refused); beyond that, and for NaN / inf, the result is some
+// index far outside the frame on either side, which is all fixed_coord() guarantees there too (border value).
+__device__ __forceinline__ FixedCoord fixed_coord_fast(float mapx, float mapy) {
+    constexpr int MAGIC = 0x4B400000;                               // bits of 12582912.0f = 1.5 * 2^23
+    const int bx = __float_as_int(__fmaf_rn(mapx, 32.0f, 12582912.0f));
+    const int by = __float_as_int(__fmaf_rn(mapy, 32.0f, 12582912.0f));
+    FixedCoord c;
+    c.ix = (bx - MAGIC) >> 5;
+    c.iy = (by - MAGIC) >> 5;
+    c.fx = bx & 31;
+    c.fy = by & 31;
+    return c;
+}
+// float(k) for 0 <= k < 2^23 without an I2F conversion
+__device__ __forceinline__ float small_int_to_float(int k) { return __int_as_float(0x4B000000 | k) - 8388608.0f; }
+__device__ __forceinline__ void bilinear_weights_fast(int fx, int fy, float& w00, float& w01, float& w10, float& w11) {
+    const float tx = small_int_to_float(fx) * 0.03125f, ty = small_int_to_float(fy) * 0.03125f;     // exact
+    const float ux = 1.0f - tx, uy = 1.0f - ty;                                                       // exact
+    w00 = fmul(uy, ux); w01 = fmul(uy, tx); w10 = fmul(ty, ux); w11 = fmul(ty, tx);
+}
+
 // per-pixel interpolation weights, computed once and applied to every frame of the launch
 template <typename SrcT> struct Weights {        // float32 / uint16 / float64 images: OpenCV's float32 table entry
     float w00, w01, w10, w11;
-    __device__ __forceinline__ void set(const FixedCoord& c) { bilinear_weights(c.fx, c.fy, w00, w01, w10, w11); }
+    __device__ __forceinline__ void set(const FixedCoord& c) { bilinear_weights_fast(c.fx, c.fy, w00, w01, w10, w11); }
+    // the same four values from the 32 x 32 table OpenCV itself uses (BilinearTab_f), built once per context on the host:
+    // one 16-byte load (L1-resident, 16 KB) instead of a dozen instructions
+    __device__ __forceinline__ void lookup(const FixedCoord& c, const float4* tab) {
+        const float4 w = __ldg(tab + ((c.fy << 5) | c.fx));
+        w00 = w.x; w01 = w.y; w10 = w.z; w11 = w.w;
+    }
 };
 template <> struct Weights<uint8_t> {            // uint8 images: int16 fixed-point weights
     int fx, fy;
     __device__ __forceinline__ void set(const FixedCoord& c) { fx = c.fx; fy = c.fy; }
+    __device__ __forceinline__ void lookup(const FixedCoord& c, const float4*) { fx = c.fx; fy = c.fy; }
 };
 
 template <typename SrcT, typename DstT> struct Blend;
@@ -138,7 +171,7 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
             mx = __ldg(a.mapx + v * W + u);
             my = __ldg(a.mapy + v * W + u);
         }
-        const FixedCoord c = fixed_coord(mx, my);
+        const FixedCoord c = fixed_coord_fast(mx, my);
         const bool inner = (unsigned)c.ix < (unsigned)(W - 1) && (unsigned)c.iy < (unsigned)(H - 1);
         off[j] = inner ? c.iy * W + c.ix : 0;
         cix[j] = c.ix; ciy[j] = c.iy;
@@ -183,35 +216,42 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Tiled variant (float32 sources — the chain): the source window of a 64x16 output tile is staged in shared memory
-// by ONE TMA box per frame, and the four neighbours are gathered from there.  The L1 path above spends ~8 L1
-// wavefronts per 32 pixels on the gather (unaligned, two rows) and is bound by them; shared memory serves the same
-// gather in ~4-5 conflict-free wavefronts, TMA moves whole lines, and the frames of a launch are double-buffered so
-// the box of frame f+1 lands while frame f is blended.
-//   * coordinates / weights / shared offsets of the tile's pixels are computed once (4 pixels per thread);
-//   * the exact bounding box of the tile's source window comes from a block-wide min/max (REDUX + shared atomics);
-//     box origin = (min ix rounded down to 4 columns — TMA's 16-byte rule —, min iy).  If the window does not fit the
-//     fixed 80x32 box (very strong distortion) the tile falls back to global gathers: correct for any map;
+// Tiled variant (float32 sources — the chain; uint16 / uint8 batches): the source window of a 64x16 output tile is
+// staged in shared memory by ONE TMA box per frame, the four neighbours are gathered from there, and the finished
+// output tile leaves through shared memory as ONE TMA store per frame (cp.async.bulk.tensor, bounds-clipped by the
+// hardware at the frame / roi edge).  The L1 path above spends ~8 L1 wavefronts per 32 pixels on the gather (unaligned,
+// two rows) and is bound by them; shared memory serves the same gather in ~4-5 conflict-free wavefronts, TMA moves whole
+// lines, and the frames of a launch are ring-buffered so the box of frame f+1 lands while frame f is blended.
+//   * the box position is ESTIMATED first by one warp from eight perimeter pixels of the tile (exact coordinates, a
+//     3-pixel margin) and the boxes of the first frames are issued at once, so the DRAM latency of the first box
+//     overlaps the coordinate phase of the whole tile (a single frame per launch used to serialise coordinates ->
+//     TMA wait -> blend per CTA: 61 us per 4096x3000 frame, latency bound);
+//   * coordinates / weights / shared offsets of the tile's pixels are then computed once (4 pixels per thread) and the
+//     exact bounding box of the tile's source window (REDUX + shared atomics) is checked against the estimated box; a
+//     tile whose window is not inside it (never seen with the margin; any map is legal) or does not fit a box at all
+//     (stronger distortion than the launch geometry was chosen for) falls back to global gathers: correct for any map;
 //   * rim pixels (window touching the frame border) are redone from global memory with per-neighbour border handling.
-#ifndef KT_TW_V
-#define KT_TW_V 64
-#define KT_TH_V 16
-#define KT_BW_V 80
-#define KT_BH_V 32
-#endif
-constexpr int KT_TW = KT_TW_V, KT_TH = KT_TH_V, KT_THREADS = 256, KT_PX = KT_TW * KT_TH / KT_THREADS;
-constexpr int KT_BW = KT_BW_V, KT_BH = KT_BH_V;
-// box width per source type: 16-byte origin granularity costs up to 3 / 7 / 15 extra columns (float32 / uint16 / uint8)
-template <typename SrcT> struct KtBox { static constexpr int BW = sizeof(SrcT) == 1 ? KT_BW + 16 : KT_BW, GRAN = 16 / (int)sizeof(SrcT), BYTES = BW * KT_BH * (int)sizeof(SrcT); };
+template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeom {
+    static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, NBUF = NBUF_, MINB = MINB_;
+};
 #ifndef KT_NBUF_V
 #define KT_NBUF_V 4
 #endif
 #ifndef KT_MINB_V
 #define KT_MINB_V 4
 #endif
-constexpr int KT_NBUF = KT_NBUF_V;                       // frames of a launch in flight per tile
-template <typename SrcT> constexpr int kt_smem() { return KT_NBUF * KtBox<SrcT>::BYTES + 128; }
-
+typedef KtGeom<64, 16, 80, 32, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens
+typedef KtGeom<64, 16, 112, 48, 2, 4> KtG1;                      // strong distortion (window up to ~1.5 x the tile)
+typedef KtGeom<32, 16, 112, 64, 2, 4> KtG2;                      // extreme distortion / large shear
+constexpr int KT_THREADS = 256;
+constexpr int KT_MARGIN = 3;                                     // pixels added around the estimated window
+// box width per source type: 16-byte origin granularity costs up to 3 / 7 / 15 extra columns (float32 / uint16 / uint8)
+template <typename SrcT, typename G> struct KtBox {
+    static constexpr int BW = sizeof(SrcT) == 1 ? G::BW + 16 : G::BW, GRAN = 16 / (int)sizeof(SrcT), BYTES = BW * G::BH * (int)sizeof(SrcT);
+};
+template <typename SrcT, typename DstT, typename G, bool TSTORE> constexpr int kt_smem() {
+    return G::NBUF * KtBox<SrcT, G>::BYTES + 128 + (TSTORE ? 2 * G::TW * G::TH * (int)sizeof(DstT) : 0);
+}
 
 // predicated global store: a plain `if (flag) *p = v` lets ptxas wrap the whole gather of that pixel in a branch
 __device__ __forceinline__ void st_if(float* p, float v, unsigned flag) {
@@ -227,26 +267,9 @@ __device__ __forceinline__ void st_if(uint8_t* p, uint8_t v, unsigned flag) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" ::"l"(p), "r"((unsigned)v), "r"(flag) : "memory");
 }
 
-template <typename SrcT, typename DstT, int MODE>
-__global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, K2Args a) {
-    constexpr int BW = KtBox<SrcT>::BW, KT_BOX_BYTES = KtBox<SrcT>::BYTES;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full = (uint64_t*)(smem + KT_NBUF * KT_BOX_BYTES);
-    int* red = (int*)(smem + KT_NBUF * KT_BOX_BYTES + 64);     // min ix, max ix, min iy, max iy
-    const int tid = threadIdx.x;
-    const int c = tid % KT_TW, r0 = tid / KT_TW;               // rows r0 + 4j
-    const int ox = blockIdx.x * KT_TW + c;
-    const int oy0 = blockIdx.y * KT_TH + r0;
-    const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
-    const int u = (ox < ow ? ox : ow - 1) + a.x0;
-    const SrcT bval = border_cast<SrcT>(a.border);
-
-    if (tid == 0) {
-        for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
-        red[0] = 0x7fffffff; red[1] = -1; red[2] = 0x7fffffff; red[3] = -1;
-        mbar_init_fence();
-    }
-    LensConst L = a.lens;
+struct KtLens { LensConst L; };
+template <int MODE> __device__ __forceinline__ void kt_load_lens(const K2Args& a, LensConst& L) {
+    L = a.lens;
     if (MODE == 2) {
         const double2* lp = reinterpret_cast<const double2*>(a.lens_dev);
         double2 q;
@@ -259,68 +282,166 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
         q = __ldg(lp + 6); L.ir[2] = q.x; L.ir[4] = q.y;
         q = __ldg(lp + 7); L.ir[5] = q.x;
     }
+}
+// fixed-point source coordinate of output pixel (u, v) (full-frame coordinates)
+template <int MODE> __device__ __forceinline__ FixedCoord kt_coord(const K2Args& a, const LensConst& L, int u, int v, double dv, double xc, double xc2) {
+    float mx, my;
+    if (MODE == 2) {
+        const double y = fma(dv, L.ir[4], L.ir[5]);                 // dv == (double)v
+        map_distort(L, xc, y, xc2, dmul(y, y), mx, my);
+    } else if (MODE == 1) {
+        undistort_map(L, u, v, mx, my);
+    } else {
+        mx = __ldg(a.mapx + v * a.W + u);
+        my = __ldg(a.mapy + v * a.W + u);
+    }
+    return fixed_coord_fast(mx, my);
+}
+
+template <typename SrcT, typename DstT, int MODE, typename G, bool TSTORE>
+__global__ void __launch_bounds__(KT_THREADS, G::MINB)
+k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, K2Args a) {
+    constexpr int KT_TW = G::TW, KT_TH = G::TH, KT_BH = G::BH, KT_NBUF = G::NBUF;
+    constexpr int KT_PX = KT_TW * KT_TH / KT_THREADS, KT_RSTEP = KT_THREADS / KT_TW;
+    constexpr int BW = KtBox<SrcT, G>::BW, KT_BOX_BYTES = KtBox<SrcT, G>::BYTES, GRAN = KtBox<SrcT, G>::GRAN;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = (uint64_t*)(smem + KT_NBUF * KT_BOX_BYTES);
+    DstT* otile = (DstT*)(smem + KT_NBUF * KT_BOX_BYTES + 128); // [2][TH][TW] when TSTORE
+    const int tid = threadIdx.x;
+    const int c = tid % KT_TW, r0 = tid / KT_TW;               // rows r0 + RSTEP * j
+    const int tx0 = blockIdx.x * KT_TW, ty0 = blockIdx.y * KT_TH;
+    const int ox = tx0 + c;
+    const int oy0 = ty0 + r0;
+    const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
+    const int u = (ox < ow ? ox : ow - 1) + a.x0;
+
+    if (tid == 0) {
+        for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
+        mbar_init_fence();
+    }
+    LensConst L;
+    kt_load_lens<MODE>(a, L);
+    auto issue = [&](int f, int bx, int by) {
+        uint64_t* bar = &full[f % KT_NBUF];
+        mbar_expect_tx(bar, KT_BOX_BYTES);
+        tma_load_3d(smem + (f % KT_NBUF) * KT_BOX_BYTES, &tm_src, bar, bx, by, f);
+    };
+    // ---- the staged box: position ESTIMATED from nine sample pixels of the tile (3 x 3: corners, edge midpoints, centre;
+    // exact coordinates, KT_MARGIN pixels added all round).  Every warp evaluates the same nine pixels in its first lanes
+    // (no shared memory, no barrier), thread 0 issues the boxes of the first frames at once: their DRAM latency overlaps
+    // the coordinate phase below.  The box is clamped to the frame, so "inside the box" implies "all four neighbours exist".
+    int bx, by;
+    bool have_box;
+    {
+        const int lane = tid & 31;
+        const int x1 = (tx0 + KT_TW <= ow ? tx0 + KT_TW : ow) - 1, y1 = (ty0 + KT_TH <= oh ? ty0 + KT_TH : oh) - 1;
+        const int kx = lane % 3, ky = (lane / 3) % 3;
+        const int sx = kx == 0 ? tx0 : (kx == 1 ? x1 : (tx0 + x1) / 2);
+        const int sy = ky == 0 ? ty0 : (ky == 1 ? y1 : (ty0 + y1) / 2);
+        int ex0 = 0x7fffffff, ex1 = -1, ey0 = 0x7fffffff, ey1 = -1;
+        if (lane < 9) {
+            const int su = sx + a.x0, sv = sy + a.y0;
+            const double sxc = MODE == 2 ? fma((double)su, L.ir[0], L.ir[2]) : 0.0;
+            const FixedCoord fc = kt_coord<MODE>(a, L, su, sv, (double)sv, sxc, dmul(sxc, sxc));
+            if (!(fc.ix < -1 || fc.ix > W - 1 || fc.iy < -1 || fc.iy > H - 1)) {       // outside the frame: nothing to stage
+                const int qx = fc.ix < 0 ? 0 : (fc.ix > W - 2 ? W - 2 : fc.ix), qy = fc.iy < 0 ? 0 : (fc.iy > H - 2 ? H - 2 : fc.iy);
+                ex0 = ex1 = qx; ey0 = ey1 = qy;
+            }
+        }
+        ex0 = __reduce_min_sync(0xffffffffu, ex0); ex1 = __reduce_max_sync(0xffffffffu, ex1);
+        ey0 = __reduce_min_sync(0xffffffffu, ey0); ey1 = __reduce_max_sync(0xffffffffu, ey1);
+        bx = ex0 - KT_MARGIN; by = ey0 - KT_MARGIN;
+        bx = (bx < 0 ? 0 : bx) & ~(GRAN - 1);
+        by = by < 0 ? 0 : by;
+        have_box = ex1 >= 0 && (ex1 + 1 + KT_MARGIN - bx) < BW && (ey1 + 1 + KT_MARGIN - by) < KT_BH && W >= 2 && H >= 2;
+        if (tid == 0 && have_box)
+            for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f, bx, by);
+    }
+    // a pixel reads its 2 x 2 window from the box iff  bx <= ix < bx + limx  and  by <= iy < by + limy
+    const unsigned limx = have_box ? (unsigned)((bx + BW - 1 < W - 1 ? bx + BW - 1 : W - 1) - bx) : 0u;
+    const unsigned limy = have_box ? (unsigned)((by + KT_BH - 1 < H - 1 ? by + KT_BH - 1 : H - 1) - by) : 0u;
+
     double xc = 0.0, xc2 = 0.0;
     if (MODE == 2) {
         xc = fma((double)u, L.ir[0], L.ir[2]);
         xc2 = dmul(xc, xc);
     }
-    int cix[KT_PX], ciy[KT_PX];
+    int so[KT_PX];
     Weights<SrcT> wt[KT_PX];
-    unsigned rim = 0, fast = 0;
-    int mnx = 0x7fffffff, mxx = -1, mny = 0x7fffffff, mxy = -1;
+    unsigned fast = 0, slow = 0;
+    // (double)v of the thread's rows by exact additions: one I2F per thread instead of one per pixel.  Rows / columns
+    // beyond the output window are not clamped for the analytic map: such pixels are never stored or gathered.
+    const double dv0 = (double)(oy0 + a.y0);
+    const bool col_live = ox < ow;
 #pragma unroll
     for (int j = 0; j < KT_PX; ++j) {
-        const int oy = oy0 + j * (KT_THREADS / KT_TW);
-        const int v = (oy < oh ? oy : oh - 1) + a.y0;
-        float mx, my;
-        if (MODE == 2) {
-            const double y = fma((double)v, L.ir[4], L.ir[5]);
-            map_distort(L, xc, y, xc2, dmul(y, y), mx, my);
-        } else if (MODE == 1) {
-            undistort_map(L, u, v, mx, my);
-        } else {
-            mx = __ldg(a.mapx + v * W + u);
-            my = __ldg(a.mapy + v * W + u);
-        }
-        const FixedCoord fc = fixed_coord(mx, my);
-        cix[j] = fc.ix; ciy[j] = fc.iy;
-        wt[j].set(fc);
-        const bool live = ox < ow && oy < oh;
-        const bool inner = (unsigned)fc.ix < (unsigned)(W - 1) && (unsigned)fc.iy < (unsigned)(H - 1);
-        if (live && inner) {
-            fast |= 1u << j;
-            mnx = min(mnx, fc.ix); mxx = max(mxx, fc.ix); mny = min(mny, fc.iy); mxy = max(mxy, fc.iy);
-        } else if (live) {
-            rim |= 1u << j;
-        }
+        const int oy = oy0 + j * KT_RSTEP;
+        const int v = (MODE == 0 ? (oy < oh ? oy : oh - 1) : oy) + a.y0;
+        const FixedCoord fc = kt_coord<MODE>(a, L, u, v, dadd(dv0, (double)(j * KT_RSTEP)), xc, xc2);
+        wt[j].lookup(fc, a.wtab);
+        const int dx = fc.ix - bx, dy = fc.iy - by;
+        const bool live = col_live && oy < oh;
+        const bool inb = (unsigned)dx < limx && (unsigned)dy < limy;
+        so[j] = inb ? dy * BW + dx : 0;
+        if (live && inb) fast |= 1u << j;
+        if (live && !inb) slow |= 1u << j;
     }
-    __syncthreads();                                   // red[] and the barriers are initialised
-    mnx = __reduce_min_sync(0xffffffffu, mnx); mxx = __reduce_max_sync(0xffffffffu, mxx);
-    mny = __reduce_min_sync(0xffffffffu, mny); mxy = __reduce_max_sync(0xffffffffu, mxy);
-    if ((tid & 31) == 0) { atomicMin(&red[0], mnx); atomicMax(&red[1], mxx); atomicMin(&red[2], mny); atomicMax(&red[3], mxy); }
-    __syncthreads();
-    const int bx = red[0] & ~(KtBox<SrcT>::GRAN - 1), by = red[2];
-    const bool any = red[1] >= 0;
-    const bool fits = any && (red[1] + 1 - bx) < BW && (red[3] + 1 - by) < KT_BH;
+    __syncthreads();                                   // the barriers are initialised for everyone
 
-    DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
-    const int dstep = (KT_THREADS / KT_TW) * ow;
+    // pixels outside the box (frame rim: window touching or leaving the frame; a tile the box does not cover): per-neighbour
+    // border handling from global memory, coordinates recomputed — rare, kept off the hot path
+    auto slow_pixel = [&](const SrcT* src, int j) -> DstT {
+        LensConst L2;
+        kt_load_lens<MODE>(a, L2);
+        const int oy = oy0 + j * KT_RSTEP;
+        const int v = (MODE == 0 ? (oy < oh ? oy : oh - 1) : oy) + a.y0;
+        const double sxc = MODE == 2 ? fma((double)u, L2.ir[0], L2.ir[2]) : 0.0;
+        const FixedCoord fc = kt_coord<MODE>(a, L2, u, v, (double)v, sxc, dmul(sxc, sxc));
+        Weights<SrcT> w;
+        w.set(fc);
+        return remap_rim<SrcT, DstT>(src, H, W, fc.ix, fc.iy, w, border_cast<SrcT>(a.border));
+    };
+
     const int src_stride = H * W, dst_stride = oh * ow;
-    if (fits) {
-        int so[KT_PX];
-#pragma unroll
-        for (int j = 0; j < KT_PX; ++j) {
-            so[j] = (fast & (1u << j)) ? (ciy[j] - by) * BW + (cix[j] - bx) : 0;
-            asm volatile("" : "+r"(so[j]));            // keep the offset: ptxas otherwise recomputes it from cix / ciy every frame
-        }
-        auto issue = [&](int f) {
-            uint64_t* bar = &full[f % KT_NBUF];
-            mbar_expect_tx(bar, KT_BOX_BYTES);
-            tma_load_3d(smem + (f % KT_NBUF) * KT_BOX_BYTES, &tm_src, bar, bx, by, f);
-        };
-        if (tid == 0) for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f);
+    const SrcT* src = (const SrcT*)a.src;
+    if (TSTORE) {
+        // every pixel of the tile goes through the shared output tile and leaves in one TMA store per frame
+        const int oo = r0 * KT_TW + c;
 #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
+            DstT* ot = otile + (f & 1) * (KT_TW * KT_TH) + oo;
+            if (have_box) {
+                mbar_wait(&full[f % KT_NBUF], (f / KT_NBUF) & 1);
+                const SrcT* box = (const SrcT*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
+#pragma unroll
+                for (int j = 0; j < KT_PX; ++j) {
+                    const SrcT* p = box + so[j];
+                    ot[j * KT_RSTEP * KT_TW] = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                }
+            }
+            if (slow) {
+#pragma unroll 1
+                for (int j = 0; j < KT_PX; ++j)
+                    if (slow & (1u << j)) ot[j * KT_RSTEP * KT_TW] = slow_pixel(src, j);
+            }
+            fence_proxy_async_smem();                  // generic-proxy writes of the tile -> visible to the TMA store
+            if (tid == 0) tma_store_wait_read<0>();    // the store of frame f-1 has read its tile: the other buffer is free again
+            __syncthreads();                           // tile complete; everyone is done with this source box
+            if (tid == 0) {
+                tma_store_3d(&tm_dst, otile + (f & 1) * (KT_TW * KT_TH), tx0, ty0, f);
+                tma_store_commit();
+                if (have_box && f + KT_NBUF < nf) issue(f + KT_NBUF, bx, by);
+            }
+            src += src_stride;
+        }
+        if (tid == 0) tma_store_wait_read<0>();
+        return;
+    }
+    DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
+    const int dstep = KT_RSTEP * ow;
+#pragma unroll 1
+    for (int f = 0; f < nf; ++f) {
+        if (have_box) {
             mbar_wait(&full[f % KT_NBUF], (f / KT_NBUF) & 1);
             const SrcT* box = (const SrcT*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
 #pragma unroll
@@ -329,34 +450,18 @@ __global__ void __launch_bounds__(KT_THREADS, KT_MINB_V) k2_tiled_kernel(const _
                 const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
                 st_if(dst + j * dstep, r, fast & (1u << j));            // predicated store, no branch around the gather
             }
-            dst += dst_stride;
+        }
+        if (slow) {
+#pragma unroll 1
+            for (int j = 0; j < KT_PX; ++j)
+                if (slow & (1u << j)) dst[j * dstep] = slow_pixel(src, j);
+        }
+        if (have_box) {
             __syncthreads();                           // everyone is done with this buffer
-            if (tid == 0 && f + KT_NBUF < nf) issue(f + KT_NBUF);
+            if (tid == 0 && f + KT_NBUF < nf) issue(f + KT_NBUF, bx, by);
         }
-    } else if (any) {
-        // the source window of this tile does not fit the staged box: gather from global memory
-        const SrcT* src = (const SrcT*)a.src;
-        for (int f = 0; f < nf; ++f) {
-#pragma unroll
-            for (int j = 0; j < KT_PX; ++j)
-                if (fast & (1u << j)) {
-                    const SrcT* p = src + (ciy[j] * W + cix[j]);
-                    dst[j * dstep] = Blend<SrcT, DstT>::run(__ldg(p), __ldg(p + 1), __ldg(p + W), __ldg(p + W + 1), wt[j]);
-                }
-            src += src_stride;
-            dst += dst_stride;
-        }
-    }
-    if (rim) {
-        const SrcT* src = (const SrcT*)a.src;
-        DstT* d2 = (DstT*)a.dst + (oy0 * ow + ox);
-        for (int f = 0; f < nf; ++f) {
-#pragma unroll
-            for (int j = 0; j < KT_PX; ++j)
-                if (rim & (1u << j)) d2[j * dstep] = remap_rim<SrcT, DstT>(src, H, W, cix[j], ciy[j], wt[j], bval);
-            src += src_stride;
-            d2 += dst_stride;
-        }
+        src += src_stride;
+        dst += dst_stride;
     }
 }
 
@@ -369,17 +474,75 @@ static bool k2_tiled_eligible(const K2Args& a, int src_dtype, int dst_dtype) {
     return tensor_map_encoder() != nullptr;
 }
 
+template <typename T> static CUtensorMapDataType kt_dtype() {
+    return sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+         : sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+}
+
+template <typename SrcT, typename DstT, typename G, bool TSTORE>
+static cudaError_t launch_tiled_g(const K2Args& a, cudaStream_t st) {
+    CUtensorMap tm, td;
+    if (!make_tensor_map(&tm, kt_dtype<SrcT>(), sizeof(SrcT), a.src, a.W, a.H, a.n_frames, KtBox<SrcT, G>::BW, G::BH)) return cudaErrorInvalidValue;
+    td = tm;
+    if (TSTORE && !make_tensor_map(&td, kt_dtype<DstT>(), sizeof(DstT), a.dst, a.ow, a.oh, a.n_frames, G::TW, G::TH)) return cudaErrorInvalidValue;
+    dim3 grid((a.ow + G::TW - 1) / G::TW, (a.oh + G::TH - 1) / G::TH);
+    constexpr int SMEM = kt_smem<SrcT, DstT, G, TSTORE>();
+    void (*kern)(const CUtensorMap, const CUtensorMap, K2Args);
+    if (a.mapx) kern = k2_tiled_kernel<SrcT, DstT, 0, G, TSTORE>;
+    else if (a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0) kern = k2_tiled_kernel<SrcT, DstT, 2, G, TSTORE>;
+    else kern = k2_tiled_kernel<SrcT, DstT, 1, G, TSTORE>;
+    if (SMEM > 48 * 1024) {
+        cudaError_t e = cudaSuccess;
+        blocks_per_sm_cached((const void*)kern, KT_THREADS, SMEM, &e);       // opt-in to > 48 KB, once per (device, kernel)
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, KT_THREADS, SMEM, st>>>(tm, td, a);
+    return cudaGetLastError();
+}
+
 template <typename SrcT, typename DstT>
 static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
-    CUtensorMap tm;
-    const CUtensorMapDataType dt = sizeof(SrcT) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : sizeof(SrcT) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
-    if (!make_tensor_map(&tm, dt, sizeof(SrcT), a.src, a.W, a.H, a.n_frames, KtBox<SrcT>::BW, KT_BH)) return cudaErrorInvalidValue;
-    dim3 grid((a.ow + KT_TW - 1) / KT_TW, (a.oh + KT_TH - 1) / KT_TH);
-    constexpr int SMEM = kt_smem<SrcT>();
-    if (a.mapx) k2_tiled_kernel<SrcT, DstT, 0><<<grid, KT_THREADS, SMEM, st>>>(tm, a);
-    else if (a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0) k2_tiled_kernel<SrcT, DstT, 2><<<grid, KT_THREADS, SMEM, st>>>(tm, a);
-    else k2_tiled_kernel<SrcT, DstT, 1><<<grid, KT_THREADS, SMEM, st>>>(tm, a);
-    return cudaGetLastError();
+    // the output tile leaves by TMA when the destination qualifies (16-byte aligned rows), else by predicated stores
+    const bool tstore = ((size_t)a.ow * sizeof(DstT)) % 16 == 0 && ((uintptr_t)a.dst) % 16 == 0;
+    const int g = a.geometry;
+    if (tstore) {
+        if (g == 2) return launch_tiled_g<SrcT, DstT, KtG2, true>(a, st);
+        if (g == 1) return launch_tiled_g<SrcT, DstT, KtG1, true>(a, st);
+        return launch_tiled_g<SrcT, DstT, KtG0, true>(a, st);
+    }
+    if (g == 2) return launch_tiled_g<SrcT, DstT, KtG2, false>(a, st);
+    if (g == 1) return launch_tiled_g<SrcT, DstT, KtG1, false>(a, st);
+    return launch_tiled_g<SrcT, DstT, KtG0, false>(a, st);
+}
+
+// Host: the staged-box geometry a lens needs for an output window — the largest source window (plus margins) over all
+// 64x16 tiles, from the exact map at the tile perimeters' 3 x 3 sample points (the very points the kernel estimates from).
+// 0: 80x32 box, 1: 112x48, 2: 32-wide tiles with a 112x64 box.  Cached per window by the caller (imgcorr_api.cu).
+int k2_pick_geometry(const LensConst& L, int H, int W, int x0, int y0, int ow, int oh) {
+    int need_w = 0, need_h = 0;
+    const int TW = 64, TH = 16;
+    for (int ty = 0; ty < oh; ty += TH)
+        for (int tx = 0; tx < ow; tx += TW) {
+            const int x1 = (tx + TW <= ow ? tx + TW : ow) - 1, y1 = (ty + TH <= oh ? ty + TH : oh) - 1;
+            int ex0 = 0x7fffffff, ex1 = -1, ey0 = 0x7fffffff, ey1 = -1;
+            for (int k = 0; k < 9; ++k) {
+                const int sx = (k % 3) == 0 ? tx : ((k % 3) == 1 ? x1 : (tx + x1) / 2);
+                const int sy = (k / 3) == 0 ? ty : ((k / 3) == 1 ? y1 : (ty + y1) / 2);
+                float mx, my;
+                undistort_map(L, sx + x0, sy + y0, mx, my);
+                const FixedCoord fc = fixed_coord(mx, my);
+                if (fc.ix < -1 || fc.ix > W - 1 || fc.iy < -1 || fc.iy > H - 1) continue;     // outside: nothing to stage
+                const int qx = fc.ix < 0 ? 0 : (fc.ix > W - 2 ? W - 2 : fc.ix), qy = fc.iy < 0 ? 0 : (fc.iy > H - 2 ? H - 2 : fc.iy);
+                ex0 = qx < ex0 ? qx : ex0; ex1 = qx > ex1 ? qx : ex1; ey0 = qy < ey0 ? qy : ey0; ey1 = qy > ey1 ? qy : ey1;
+            }
+            if (ex1 < 0) continue;
+            const int w = ex1 - ex0 + 2 + 2 * KT_MARGIN + 3, h = ey1 - ey0 + 2 + 2 * KT_MARGIN;   // + 3: 16-byte origin (float32)
+            if (w > need_w) need_w = w;
+            if (h > need_h) need_h = h;
+        }
+    if (need_w <= KtG0::BW && need_h <= KtG0::BH) return 0;
+    if (need_w <= KtG1::BW && need_h <= KtG1::BH) return 1;
+    return 2;
 }
 
 __global__ void __launch_bounds__(256) k2_write_maps_kernel(LensConst lens, float* mapx, float* mapy, int H, int W) {

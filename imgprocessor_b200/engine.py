@@ -365,6 +365,13 @@ class Engine(object):
         return out[0] if squeeze else out
 
 
+def host_fingerprint(arr):
+    """64-bit fingerprint of a C-contiguous numpy array's bytes (imgcorr_host_fingerprint; no GPU involved)"""
+    out = ctypes.c_ulonglong(0)
+    _lib.check(_lib.lib().imgcorr_host_fingerprint(arr.ctypes.data_as(ctypes.c_void_p), arr.nbytes, ctypes.byref(out)))
+    return int(out.value)
+
+
 def pinned_empty(shape, dtype):
     """numpy array backed by page-locked memory from imgcorr_host_alloc (freed with the array)."""
     lib = _lib.lib()

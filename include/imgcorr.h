@@ -196,6 +196,11 @@ IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* ctx, const void* frames_dev, in
  * Synchronous. */
 IMGCORR_API int imgcorr_selftest_division(imgcorr_ctx* ctx, int numerators_per_divisor, unsigned long long seed, double out[2]);
 
+/* 64-bit fingerprint of a host buffer (every byte contributes; several host threads).  The Python mirror keys its
+ * "is this calibration map already on the device?" cache on it: the reference re-reads dark / flat arrays on every
+ * correct() call (camera/CameraCalibration.py:500-502, 521-526), so an array edited in place must be uploaded again. */
+IMGCORR_API int imgcorr_host_fingerprint(const void* host_ptr, size_t bytes, unsigned long long* out);
+
 /* page-locked host memory for the *_host entry points */
 IMGCORR_API int imgcorr_host_alloc(size_t bytes, void** out_ptr);
 IMGCORR_API int imgcorr_host_free(void* ptr);

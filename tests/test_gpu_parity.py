@@ -678,6 +678,10 @@ def test_calibration_modified_in_place_is_uploaded_again(ip):
     want = refpath.correct(raw, g['dark'], g['flat'], None, 0.1)
     assert not np.array_equal(out1, out2)
     assert np.abs(out2 - want).max() <= 1e-5 * 65535
+    g['dark'][11, 13] += 4000.0                                      # a single patched pixel must be noticed as well
+    out3, _ = _quiet(cal.correct, raw, threshold=0.0)
+    want = refpath.correct(raw, g['dark'], g['flat'], None, 0.0)
+    assert np.abs(out3 - want).max() <= 1e-5 * 65535
 
 
 def test_chain_overlap_mode_is_identical(ip):

@@ -102,6 +102,14 @@ def test_calibration_upload_token_sees_in_place_changes():
     assert t0 == _map_token('dark', a) and t0 != _map_token('flat', a)
     a *= 2                                       # in place: same object, new content
     assert _map_token('dark', a) != t0
+    big = np.zeros((1500, 2048), np.float32)     # every byte counts: one patched hot pixel in a large map, anywhere
+    t1 = _map_token('dark', big)
+    for pos in ((0, 0), (1499, 2047), (777, 1023), (3, 5)):
+        big[pos] = 1e-3
+        t2 = _map_token('dark', big)
+        assert t2 != t1, pos
+        t1 = t2
+    assert _map_token('dark', big.copy()) == t1  # a different object with the same content needs no new upload
     assert _map_token('dark', 3.0) is None
     b = a[::2]                                   # non-contiguous views work too
     assert _map_token('dark', b) == _map_token('dark', b)

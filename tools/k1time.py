@@ -24,6 +24,7 @@ for per in (1, 4, 32):
         e.pointwise_median(raw[:per], 0.1, 3, out=out[:per])
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    torch.cuda._sleep(40000000)          # ~20 ms: the launches below queue up behind it, so the events time the GPU, not Python
     ev[0].record()
     for i in range(reps):
         g = i % groups
