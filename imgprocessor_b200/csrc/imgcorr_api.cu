@@ -55,6 +55,12 @@ struct imgcorr_ctx {
     float4* k2_wtab = nullptr;                // OpenCV's BilinearTab_f [32][32] (K2 tiles)
     struct GeomKey { int x0, y0, ow, oh, g; };
     std::vector<GeomKey> k2_geom;             // staged-box geometry per output window (k2_pick_geometry), reset by set_lens
+    // K2 coordinate cache: packed per-pixel source coordinates of the current lens for an output window (4 bytes per pixel),
+    // written by the first tiled launch, read by the following ones; dropped by set_lens
+    struct K2Cache { int x0, y0, ow, oh, g, esz; unsigned* pack; int2* hdr; cudaEvent_t ev; cudaStream_t st; unsigned long long stamp; };
+    std::vector<K2Cache> k2_cache;
+    int k2_cache_on = 1, k2_tma_store = 0;
+    unsigned long long k2_stamp = 0;
     void* dump = nullptr;                     // scratch for stores of lanes that own no output pixel
     int raw_big_endian = 0;
     long long raw_gap = 0;
@@ -130,6 +136,15 @@ extern "C" IMGCORR_API int imgcorr_ctx_create(int device, int height, int width,
     return IMGCORR_OK;
 }
 
+static void free_k2_cache(imgcorr_ctx* c) {
+    for (auto& k : c->k2_cache) {
+        cudaFree(k.pack);
+        cudaFree(k.hdr);
+        if (k.ev) cudaEventDestroy(k.ev);
+    }
+    c->k2_cache.clear();
+}
+
 static void free_slots(imgcorr_ctx* c) {
     for (auto& s : c->slots) {
         if (s.d_raw) cudaFree(s.d_raw);
@@ -163,6 +178,7 @@ extern "C" IMGCORR_API int imgcorr_ctx_destroy(imgcorr_ctx* c) {
     cudaFree(c->mid[1]);
     cudaFree(c->lens_dev);
     cudaFree(c->k2_wtab);
+    free_k2_cache(c);
     cudaFree(c->warp_tab);
     cudaFree(c->warp_itab[0]);
     cudaFree(c->warp_itab[1]);
@@ -188,6 +204,17 @@ extern "C" IMGCORR_API int imgcorr_set_option(imgcorr_ctx* c, int key, int value
             return IMGCORR_OK;
         case IMGCORR_OPT_CHAIN_OVERLAP:
             c->chain_overlap = value ? 1 : 0;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_K2_TMA_STORE:
+            c->k2_tma_store = value ? 1 : 0;
+            return IMGCORR_OK;
+        case IMGCORR_OPT_K2_COORD_CACHE:
+            c->k2_cache_on = value ? 1 : 0;
+            if (!value && !c->k2_cache.empty()) {
+                DeviceGuard g(c->device);
+                cudaDeviceSynchronize();
+                free_k2_cache(c);
+            }
             return IMGCORR_OK;
         case IMGCORR_OPT_K3_VARIANT:
             if (value < 0 || value > 2) return fail(IMGCORR_ERR_INVALID, "k3 variant %d", value);
@@ -350,6 +377,11 @@ extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], c
     c->lens = L;
     c->has_lens = true;
     c->k2_geom.clear();
+    if (!c->k2_cache.empty()) {
+        DeviceGuard g(c->device);
+        cudaDeviceSynchronize();                       // launches that still read the old lens' coordinates
+        free_k2_cache(c);
+    }
     return IMGCORR_OK;
 }
 
@@ -422,6 +454,8 @@ static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, 
     a.border = border_for_dtype(sdt == DT_U8, sdt == DT_U16, border);
     a.lens = c->lens;
     a.lens_dev = c->lens_dev;
+    a.sm_count = c->sm_count;
+    a.tma_store = c->k2_tma_store;
     if (!c->k2_wtab) {
         std::vector<float4> t(32 * 32);
         for (int fy = 0; fy < 32; ++fy)
@@ -445,8 +479,53 @@ static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, 
             c->k2_geom.push_back({x0, y0, ow, oh, a.geometry});
         }
     }
+    // coordinate cache (tiled variant, analytic map): the first launch for this lens / window writes it, later ones read it
+    imgcorr_ctx::K2Cache* building = nullptr;
+    // Only launches of one or two frames use it: a batch amortises the analytic evaluation over its frames and the
+    // per-tile kernel then streams faster (19 vs 33 us per 4096x3000 frame) than the cached one (49 vs 65 us for one frame).
+    if (!mapx && c->k2_cache_on && n > 0 && n <= 2 && ow > 0 && oh > 0 && k2_will_tile(a, sdt, ddt, c->k2_variant)) {
+        const int esz = (int)dtype_size(sdt);
+        imgcorr_ctx::K2Cache* hit = nullptr;
+        for (auto& k : c->k2_cache)
+            if (k.x0 == x0 && k.y0 == y0 && k.ow == ow && k.oh == oh && k.g == a.geometry && k.esz == esz) { hit = &k; break; }
+        if (hit) {
+            if (hit->st != st) CK(cudaStreamWaitEvent(st, hit->ev, 0));       // written on another stream
+            hit->stamp = ++c->k2_stamp;
+            a.cpack = hit->pack; a.chdr = hit->hdr;
+        } else {
+            if (c->k2_cache.size() >= 2) {             // keep at most two windows (keep_size True / False): drop the older one
+                size_t old = c->k2_cache[0].stamp < c->k2_cache[1].stamp ? 0 : 1;
+                CK(cudaDeviceSynchronize());
+                cudaFree(c->k2_cache[old].pack); cudaFree(c->k2_cache[old].hdr);
+                if (c->k2_cache[old].ev) cudaEventDestroy(c->k2_cache[old].ev);
+                c->k2_cache.erase(c->k2_cache.begin() + old);
+            }
+            size_t words = 0, tiles = 0;
+            k2_cache_size(a.geometry, ow, oh, &words, &tiles);
+            imgcorr_ctx::K2Cache k{x0, y0, ow, oh, a.geometry, esz, nullptr, nullptr, nullptr, st, ++c->k2_stamp};
+            if (cudaMalloc((void**)&k.pack, words * sizeof(unsigned)) == cudaSuccess &&
+                cudaMalloc((void**)&k.hdr, tiles * sizeof(int2)) == cudaSuccess &&
+                cudaEventCreateWithFlags(&k.ev, cudaEventDisableTiming) == cudaSuccess) {
+                c->k2_cache.push_back(k);
+                building = &c->k2_cache.back();
+                a.cpack_w = k.pack; a.chdr_w = k.hdr;
+            } else {                                   // no memory for the cache: compute every time
+                cudaGetLastError();
+                cudaFree(k.pack); cudaFree(k.hdr);
+                if (k.ev) cudaEventDestroy(k.ev);
+            }
+        }
+    }
     int l = 0;
     cudaError_t e = launch_k2(a, sdt, ddt, c->k2_variant, st, &l);
+    if (building) {
+        if (e == cudaSuccess) e = cudaEventRecord(building->ev, st);
+        if (e != cudaSuccess) {                        // never leave a half-written cache behind
+            cudaDeviceSynchronize();
+            cudaFree(building->pack); cudaFree(building->hdr); cudaEventDestroy(building->ev);
+            c->k2_cache.pop_back();
+        }
+    }
     c->launches += l;
     if (e == cudaErrorInvalidValue && l == 0)
         return fail(IMGCORR_ERR_INVALID, "unsupported dtype pair src=%d dst=%d", sdt, ddt);

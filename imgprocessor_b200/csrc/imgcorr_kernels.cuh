@@ -56,7 +56,16 @@ struct K2Args {
     const double* lens_dev;  // device copy of the lens constants (see LensPack), loaded once per thread into registers
     int geometry;            // tiled variant: staged-box geometry (k2_pick_geometry), 0 = 80x32 box for 64x16 tiles
     const float4* wtab;      // device copy of OpenCV's 32 x 32 bilinear weight table [fy][fx] = (w00, w01, w10, w11)
+    // coordinate cache of the tiled variant (k2_undistort.cu): packed per-pixel words [tile][px][256] + box origin per tile
+    const unsigned* cpack;   // read the cache (it is complete)
+    const int2* chdr;
+    unsigned* cpack_w;       // write the cache while computing (first launch for this lens / window / geometry)
+    int2* chdr_w;
+    int sm_count;
+    int tma_store;           // tiled variant: output tile through shared memory + TMA store instead of predicated stores
 };
+void k2_cache_size(int geometry, int ow, int oh, size_t* words, size_t* tiles);
+bool k2_will_tile(const K2Args& a, int src_dtype, int dst_dtype, int variant);    // launch_k2 takes the tiled variant
 int k2_pick_geometry(const LensConst& lens, int H, int W, int x0, int y0, int ow, int oh);
 
 // order of the doubles in K2Args::lens_dev

@@ -50,6 +50,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, ui
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z) : "memory");
 }
 
+// plain (1-D) bulk copy global -> shared, 16-byte aligned, size a multiple of 16 bytes, completion on `bar`
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // tiled bulk tensor store shared -> global (bulk async-group completion); parts of the box outside the tensor are
 // not written.  Sequence: write the tile with ordinary stores, fence_proxy_async_smem() in every writing thread,
 // barrier, one thread issues the store + commit, and waits for `.read` before the tile is overwritten.

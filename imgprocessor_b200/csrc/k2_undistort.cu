@@ -16,6 +16,7 @@
 // getOptimalNewCameraMatrix always produces) x depends on the column only and is hoisted.
 #include "imgcorr_kernels.cuh"
 #include "imgcorr_tma.cuh"
+#include <stdlib.h>
 
 namespace imgcorr {
 
@@ -62,15 +63,15 @@ template <typename SrcT> struct Weights {        // float32 / uint16 / float64 i
     __device__ __forceinline__ void set(const FixedCoord& c) { bilinear_weights_fast(c.fx, c.fy, w00, w01, w10, w11); }
     // the same four values from the 32 x 32 table OpenCV itself uses (BilinearTab_f), built once per context on the host:
     // one 16-byte load (L1-resident, 16 KB) instead of a dozen instructions
-    __device__ __forceinline__ void lookup(const FixedCoord& c, const float4* tab) {
-        const float4 w = __ldg(tab + ((c.fy << 5) | c.fx));
+    __device__ __forceinline__ void lookup(unsigned fyfx, const float4* tab) {       // fyfx = fy * 32 + fx
+        const float4 w = __ldg(tab + fyfx);
         w00 = w.x; w01 = w.y; w10 = w.z; w11 = w.w;
     }
 };
 template <> struct Weights<uint8_t> {            // uint8 images: int16 fixed-point weights
     int fx, fy;
     __device__ __forceinline__ void set(const FixedCoord& c) { fx = c.fx; fy = c.fy; }
-    __device__ __forceinline__ void lookup(const FixedCoord& c, const float4*) { fx = c.fx; fy = c.fy; }
+    __device__ __forceinline__ void lookup(unsigned fyfx, const float4*) { fx = fyfx & 31; fy = fyfx >> 5; }
 };
 
 template <typename SrcT, typename DstT> struct Blend;
@@ -253,20 +254,35 @@ template <typename SrcT, typename DstT, typename G, bool TSTORE> constexpr int k
     return G::NBUF * KtBox<SrcT, G>::BYTES + 128 + (TSTORE ? 2 * G::TW * G::TH * (int)sizeof(DstT) : 0);
 }
 
-// predicated global store: a plain `if (flag) *p = v` lets ptxas wrap the whole gather of that pixel in a branch
+// predicated global store: a plain `if (flag) *p = v` lets ptxas wrap the whole gather of that pixel in a branch.
+// No "memory" clobber: these stores write output pixels that nothing in the kernel reads back, and a clobber would stop
+// the compiler from hoisting the next pixel's shared-memory gathers above this pixel's store (serialised LDS latency).
 __device__ __forceinline__ void st_if(float* p, float v, unsigned flag) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(flag) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f32 [%0], %1;\n\t}" ::"l"(p), "f"(v), "r"(flag));
 }
 __device__ __forceinline__ void st_if(double* p, double v, unsigned flag) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(flag) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.f64 [%0], %1;\n\t}" ::"l"(p), "d"(v), "r"(flag));
 }
 __device__ __forceinline__ void st_if(uint16_t* p, uint16_t v, unsigned flag) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u16 [%0], %1;\n\t}" ::"l"(p), "h"(v), "r"(flag) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u16 [%0], %1;\n\t}" ::"l"(p), "h"(v), "r"(flag));
 }
 __device__ __forceinline__ void st_if(uint8_t* p, uint8_t v, unsigned flag) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" ::"l"(p), "r"((unsigned)v), "r"(flag) : "memory");
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.global.u8 [%0], %1;\n\t}" ::"l"(p), "r"((unsigned)v), "r"(flag));
 }
 
+// predicated shared-memory store (same reason)
+__device__ __forceinline__ void sts_if(float* p, float v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f32 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "f"(v), "r"(flag));
+}
+__device__ __forceinline__ void sts_if(double* p, double v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.f64 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "d"(v), "r"(flag));
+}
+__device__ __forceinline__ void sts_if(uint16_t* p, uint16_t v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u16 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "h"(v), "r"(flag));
+}
+__device__ __forceinline__ void sts_if(uint8_t* p, uint8_t v, unsigned flag) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u8 [%0], %1;\n\t}" ::"r"(smem_u32(p)), "r"((unsigned)v), "r"(flag));
+}
 struct KtLens { LensConst L; };
 template <int MODE> __device__ __forceinline__ void kt_load_lens(const K2Args& a, LensConst& L) {
     L = a.lens;
@@ -298,98 +314,150 @@ template <int MODE> __device__ __forceinline__ FixedCoord kt_coord(const K2Args&
     return fixed_coord_fast(mx, my);
 }
 
-template <typename SrcT, typename DstT, int MODE, typename G, bool TSTORE>
+// packed per-pixel state of a tile (the coordinate cache, see below): bits 0..13 offset of the top-left neighbour inside
+// the staged box, 14..18 fx, 19..23 fy (1/32-pixel phases), bit 31 = window entirely outside the frame (the border value
+// itself, as OpenCV), bit 30 = "slow" pixel (window on the frame rim or not inside the box): redone from global memory.
+constexpr unsigned KP_OUTSIDE = 0x80000000u, KP_SLOW = 0x40000000u;
+
+// CMODE 0: coordinates computed, nothing cached (explicit maps; cache switched off)
+//       1: coordinates computed and written to the context's coordinate cache (first launch for a lens / window)
+//       2: coordinates read from the cache: 4 bytes per pixel instead of ~45 float64 operations and ~90 instructions.
+// The lens is constant per context, so the analytic evaluation — what bounds a ONE-frame launch (119 instructions per pixel,
+// 65 us per 4096x3000 frame, issue bound: profiles/r2_k2_single_analytic_ncu_full.txt) — is paid once, not once per call.
+template <typename SrcT, typename DstT, int MODE, typename G, bool TSTORE, int CMODE>
 __global__ void __launch_bounds__(KT_THREADS, G::MINB)
 k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, K2Args a) {
     constexpr int KT_TW = G::TW, KT_TH = G::TH, KT_BH = G::BH, KT_NBUF = G::NBUF;
     constexpr int KT_PX = KT_TW * KT_TH / KT_THREADS, KT_RSTEP = KT_THREADS / KT_TW;
     constexpr int BW = KtBox<SrcT, G>::BW, KT_BOX_BYTES = KtBox<SrcT, G>::BYTES, GRAN = KtBox<SrcT, G>::GRAN;
+    static_assert(BW * KT_BH <= (1 << 14), "box offset must fit 14 bits of the packed word");
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full = (uint64_t*)(smem + KT_NBUF * KT_BOX_BYTES);
+    int* est = (int*)(smem + KT_NBUF * KT_BOX_BYTES + 64);      // bx, by (bx < 0: no box)
     DstT* otile = (DstT*)(smem + KT_NBUF * KT_BOX_BYTES + 128); // [2][TH][TW] when TSTORE
     const int tid = threadIdx.x;
     const int c = tid % KT_TW, r0 = tid / KT_TW;               // rows r0 + RSTEP * j
     const int tx0 = blockIdx.x * KT_TW, ty0 = blockIdx.y * KT_TH;
+    const int tile = blockIdx.y * gridDim.x + blockIdx.x;
     const int ox = tx0 + c;
     const int oy0 = ty0 + r0;
     const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
     const int u = (ox < ow ? ox : ow - 1) + a.x0;
 
-    if (tid == 0) {
-        for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
-        mbar_init_fence();
-    }
-    LensConst L;
-    kt_load_lens<MODE>(a, L);
     auto issue = [&](int f, int bx, int by) {
         uint64_t* bar = &full[f % KT_NBUF];
         mbar_expect_tx(bar, KT_BOX_BYTES);
         tma_load_3d(smem + (f % KT_NBUF) * KT_BOX_BYTES, &tm_src, bar, bx, by, f);
     };
-    // ---- the staged box: position ESTIMATED from nine sample pixels of the tile (3 x 3: corners, edge midpoints, centre;
-    // exact coordinates, KT_MARGIN pixels added all round).  Every warp evaluates the same nine pixels in its first lanes
-    // (no shared memory, no barrier), thread 0 issues the boxes of the first frames at once: their DRAM latency overlaps
-    // the coordinate phase below.  The box is clamped to the frame, so "inside the box" implies "all four neighbours exist".
+    unsigned pk[KT_PX];
     int bx, by;
-    bool have_box;
-    {
-        const int lane = tid & 31;
-        const int x1 = (tx0 + KT_TW <= ow ? tx0 + KT_TW : ow) - 1, y1 = (ty0 + KT_TH <= oh ? ty0 + KT_TH : oh) - 1;
-        const int kx = lane % 3, ky = (lane / 3) % 3;
-        const int sx = kx == 0 ? tx0 : (kx == 1 ? x1 : (tx0 + x1) / 2);
-        const int sy = ky == 0 ? ty0 : (ky == 1 ? y1 : (ty0 + y1) / 2);
-        int ex0 = 0x7fffffff, ex1 = -1, ey0 = 0x7fffffff, ey1 = -1;
-        if (lane < 9) {
-            const int su = sx + a.x0, sv = sy + a.y0;
-            const double sxc = MODE == 2 ? fma((double)su, L.ir[0], L.ir[2]) : 0.0;
-            const FixedCoord fc = kt_coord<MODE>(a, L, su, sv, (double)sv, sxc, dmul(sxc, sxc));
-            if (!(fc.ix < -1 || fc.ix > W - 1 || fc.iy < -1 || fc.iy > H - 1)) {       // outside the frame: nothing to stage
-                const int qx = fc.ix < 0 ? 0 : (fc.ix > W - 2 ? W - 2 : fc.ix), qy = fc.iy < 0 ? 0 : (fc.iy > H - 2 ? H - 2 : fc.iy);
-                ex0 = ex1 = qx; ey0 = ey1 = qy;
+    if (CMODE == 2) {
+        // ---- cached coordinates: the box position comes with the tile, its boxes are issued before anything else ----
+        const int2 hdr = __ldg(a.chdr + tile);
+        bx = hdr.x; by = hdr.y;
+        if (tid == 0) {
+            for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
+            mbar_init_fence();
+            if (bx >= 0) for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f, bx, by);
+        }
+        const unsigned* cp = a.cpack + ((size_t)tile * KT_PX) * KT_THREADS + tid;
+#pragma unroll
+        for (int j = 0; j < KT_PX; ++j) pk[j] = __ldg(cp + j * KT_THREADS);
+    } else {
+        if (tid == 0) {
+            for (int b = 0; b < KT_NBUF; ++b) mbar_init(&full[b], 1);
+            mbar_init_fence();
+        }
+        LensConst L;
+        kt_load_lens<MODE>(a, L);
+        // ---- the staged box: position ESTIMATED by warp 0 from nine sample pixels of the tile (3 x 3: corners, edge
+        // midpoints, centre; exact coordinates, KT_MARGIN pixels added all round) and clamped to the frame, so that
+        // "inside the box" implies "all four neighbours exist".  Thread 0 issues the boxes of the first frames at once:
+        // their DRAM latency overlaps the coordinate phase of the other warps.
+        if (tid < 32) {
+            const int x1 = (tx0 + KT_TW <= ow ? tx0 + KT_TW : ow) - 1, y1 = (ty0 + KT_TH <= oh ? ty0 + KT_TH : oh) - 1;
+            const int kx = tid % 3, ky = (tid / 3) % 3;
+            const int sx = kx == 0 ? tx0 : (kx == 1 ? x1 : (tx0 + x1) / 2);
+            const int sy = ky == 0 ? ty0 : (ky == 1 ? y1 : (ty0 + y1) / 2);
+            int ex0 = 0x7fffffff, ex1 = -1, ey0 = 0x7fffffff, ey1 = -1;
+            if (tid < 9) {
+                const int su = sx + a.x0, sv = sy + a.y0;
+                const double sxc = MODE == 2 ? fma((double)su, L.ir[0], L.ir[2]) : 0.0;
+                const FixedCoord fc = kt_coord<MODE>(a, L, su, sv, (double)sv, sxc, dmul(sxc, sxc));
+                if (!(fc.ix < -1 || fc.ix > W - 1 || fc.iy < -1 || fc.iy > H - 1)) {       // outside the frame: nothing to stage
+                    const int qx = fc.ix < 0 ? 0 : (fc.ix > W - 2 ? W - 2 : fc.ix), qy = fc.iy < 0 ? 0 : (fc.iy > H - 2 ? H - 2 : fc.iy);
+                    ex0 = ex1 = qx; ey0 = ey1 = qy;
+                }
+            }
+            ex0 = __reduce_min_sync(0xffffffffu, ex0); ex1 = __reduce_max_sync(0xffffffffu, ex1);
+            ey0 = __reduce_min_sync(0xffffffffu, ey0); ey1 = __reduce_max_sync(0xffffffffu, ey1);
+            int ebx = ex0 - KT_MARGIN, eby = ey0 - KT_MARGIN;
+            ebx = (ebx < 0 ? 0 : ebx) & ~(GRAN - 1);
+            eby = eby < 0 ? 0 : eby;
+            const bool have = ex1 >= 0 && (ex1 + 1 + KT_MARGIN - ebx) < BW && (ey1 + 1 + KT_MARGIN - eby) < KT_BH && W >= 2 && H >= 2;
+            if (tid == 0) {
+                if (have) for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f, ebx, eby);
+                est[0] = have ? ebx : -1; est[1] = eby;
+                if (CMODE == 1) a.chdr_w[tile] = make_int2(have ? ebx : -1, eby);
             }
         }
-        ex0 = __reduce_min_sync(0xffffffffu, ex0); ex1 = __reduce_max_sync(0xffffffffu, ex1);
-        ey0 = __reduce_min_sync(0xffffffffu, ey0); ey1 = __reduce_max_sync(0xffffffffu, ey1);
-        bx = ex0 - KT_MARGIN; by = ey0 - KT_MARGIN;
-        bx = (bx < 0 ? 0 : bx) & ~(GRAN - 1);
-        by = by < 0 ? 0 : by;
-        have_box = ex1 >= 0 && (ex1 + 1 + KT_MARGIN - bx) < BW && (ey1 + 1 + KT_MARGIN - by) < KT_BH && W >= 2 && H >= 2;
-        if (tid == 0 && have_box)
-            for (int f = 0; f < KT_NBUF && f < nf; ++f) issue(f, bx, by);
+        double xc = 0.0, xc2 = 0.0;
+        if (MODE == 2) {
+            xc = fma((double)u, L.ir[0], L.ir[2]);
+            xc2 = dmul(xc, xc);
+        }
+        // (double)v of the thread's rows by exact additions: one I2F per thread instead of one per pixel.  Rows / columns
+        // beyond the output window are not clamped for the analytic map: such pixels are never stored or gathered.
+        const double dv0 = (double)(oy0 + a.y0);
+        int cix[KT_PX], ciy[KT_PX];
+#pragma unroll
+        for (int j = 0; j < KT_PX; ++j) {
+            const int oy = oy0 + j * KT_RSTEP;
+            const int v = (MODE == 0 ? (oy < oh ? oy : oh - 1) : oy) + a.y0;
+            const FixedCoord fc = kt_coord<MODE>(a, L, u, v, dadd(dv0, (double)(j * KT_RSTEP)), xc, xc2);
+            cix[j] = fc.ix; ciy[j] = fc.iy;
+            pk[j] = (unsigned)(fc.fx << 14) | (unsigned)(fc.fy << 19);
+        }
+        __syncthreads();                               // the estimate is published (and the barriers are initialised)
+        bx = est[0]; by = est[1];
+        // a pixel reads its 2 x 2 window from the box iff  bx <= ix < bx + limx  and  by <= iy < by + limy
+        const unsigned limx = bx >= 0 ? (unsigned)((bx + BW - 1 < W - 1 ? bx + BW - 1 : W - 1) - bx) : 0u;
+        const unsigned limy = bx >= 0 ? (unsigned)((by + KT_BH - 1 < H - 1 ? by + KT_BH - 1 : H - 1) - by) : 0u;
+#pragma unroll
+        for (int j = 0; j < KT_PX; ++j) {
+            const int dx = cix[j] - bx, dy = ciy[j] - by;
+            const bool inb = (unsigned)dx < limx && (unsigned)dy < limy;
+            const bool outside = cix[j] >= W || cix[j] + 1 < 0 || ciy[j] >= H || ciy[j] + 1 < 0;
+            pk[j] |= inb ? (unsigned)(dy * BW + dx) : (outside ? KP_OUTSIDE : KP_SLOW);
+        }
+        if (CMODE == 1) {
+            unsigned* cp = a.cpack_w + ((size_t)tile * KT_PX) * KT_THREADS + tid;
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j) cp[j * KT_THREADS] = pk[j];
+        }
     }
-    // a pixel reads its 2 x 2 window from the box iff  bx <= ix < bx + limx  and  by <= iy < by + limy
-    const unsigned limx = have_box ? (unsigned)((bx + BW - 1 < W - 1 ? bx + BW - 1 : W - 1) - bx) : 0u;
-    const unsigned limy = have_box ? (unsigned)((by + KT_BH - 1 < H - 1 ? by + KT_BH - 1 : H - 1) - by) : 0u;
-
-    double xc = 0.0, xc2 = 0.0;
-    if (MODE == 2) {
-        xc = fma((double)u, L.ir[0], L.ir[2]);
-        xc2 = dmul(xc, xc);
-    }
+    const bool have_box = bx >= 0;
+    // ---- unpack: shared-memory offset, the four weights (OpenCV's own 32 x 32 table, L1-resident), pixel classes ----
     int so[KT_PX];
     Weights<SrcT> wt[KT_PX];
-    unsigned fast = 0, slow = 0;
-    // (double)v of the thread's rows by exact additions: one I2F per thread instead of one per pixel.  Rows / columns
-    // beyond the output window are not clamped for the analytic map: such pixels are never stored or gathered.
-    const double dv0 = (double)(oy0 + a.y0);
+    unsigned fast = 0, slow = 0, outm = 0;
     const bool col_live = ox < ow;
 #pragma unroll
     for (int j = 0; j < KT_PX; ++j) {
-        const int oy = oy0 + j * KT_RSTEP;
-        const int v = (MODE == 0 ? (oy < oh ? oy : oh - 1) : oy) + a.y0;
-        const FixedCoord fc = kt_coord<MODE>(a, L, u, v, dadd(dv0, (double)(j * KT_RSTEP)), xc, xc2);
-        wt[j].lookup(fc, a.wtab);
-        const int dx = fc.ix - bx, dy = fc.iy - by;
-        const bool live = col_live && oy < oh;
-        const bool inb = (unsigned)dx < limx && (unsigned)dy < limy;
-        so[j] = inb ? dy * BW + dx : 0;
-        if (live && inb) fast |= 1u << j;
-        if (live && !inb) slow |= 1u << j;
+        const bool live = col_live && oy0 + j * KT_RSTEP < oh;
+        const unsigned w = pk[j];
+        so[j] = (w & (KP_OUTSIDE | KP_SLOW)) ? 0 : (int)(w & 0x3fffu);
+        wt[j].lookup((w >> 14) & 1023u, a.wtab);
+        if (live) {
+            if (w & KP_OUTSIDE) outm |= 1u << j;
+            else if (w & KP_SLOW) slow |= 1u << j;
+            else fast |= 1u << j;
+        }
     }
-    __syncthreads();                                   // the barriers are initialised for everyone
+    if (CMODE == 2) __syncthreads();                   // the barriers are initialised for everyone
 
-    // pixels outside the box (frame rim: window touching or leaving the frame; a tile the box does not cover): per-neighbour
-    // border handling from global memory, coordinates recomputed — rare, kept off the hot path
+    // "slow" pixels (window on the frame rim, or a tile the box does not cover): per-neighbour border handling from global
+    // memory with coordinates recomputed — a fraction of a percent of the pixels, kept off the hot path
     auto slow_pixel = [&](const SrcT* src, int j) -> DstT {
         LensConst L2;
         kt_load_lens<MODE>(a, L2);
@@ -401,12 +469,19 @@ k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
         w.set(fc);
         return remap_rim<SrcT, DstT>(src, H, W, fc.ix, fc.iy, w, border_cast<SrcT>(a.border));
     };
+    const DstT bout = (DstT)border_cast<SrcT>(a.border);
 
     const int src_stride = H * W, dst_stride = oh * ow;
     const SrcT* src = (const SrcT*)a.src;
     if (TSTORE) {
         // every pixel of the tile goes through the shared output tile and leaves in one TMA store per frame
         const int oo = r0 * KT_TW + c;
+        // pixels whose window lies outside the frame hold the border value in both output tiles for the whole launch
+        if (outm) {
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j)
+                if (outm & (1u << j)) { otile[oo + j * KT_RSTEP * KT_TW] = bout; otile[KT_TW * KT_TH + oo + j * KT_RSTEP * KT_TW] = bout; }
+        }
 #pragma unroll 1
         for (int f = 0; f < nf; ++f) {
             DstT* ot = otile + (f & 1) * (KT_TW * KT_TH) + oo;
@@ -416,7 +491,8 @@ k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
 #pragma unroll
                 for (int j = 0; j < KT_PX; ++j) {
                     const SrcT* p = box + so[j];
-                    ot[j * KT_RSTEP * KT_TW] = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                    const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                    sts_if(ot + j * KT_RSTEP * KT_TW, r, fast & (1u << j));
                 }
             }
             if (slow) {
@@ -451,6 +527,11 @@ k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
                 st_if(dst + j * dstep, r, fast & (1u << j));            // predicated store, no branch around the gather
             }
         }
+        if (outm) {
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j)
+                if (outm & (1u << j)) dst[j * dstep] = bout;
+        }
         if (slow) {
 #pragma unroll 1
             for (int j = 0; j < KT_PX; ++j)
@@ -465,6 +546,203 @@ k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     }
 }
 
+template <typename T> static CUtensorMapDataType kt_dtype() {
+    return sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+         : sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Cached-coordinate variant: a PERSISTENT kernel over the work items (tile, frame) of a launch, tile-major, each CTA a
+// contiguous range.  Thread 0 keeps a ring of KC_NBUF items in flight — the source box of the item (one TMA box) and,
+// for the first item of a tile, the tile's packed coordinates (one 4 KB bulk copy), both completing on the item's
+// mbarrier — so DRAM latency is covered across tiles as well as across frames: a ONE-frame launch streams like a batch
+// (the analytic kernel above serialises box latency -> blend -> store per CTA and is issue bound on top of that).
+// Per item: wait, (new tile: unpack offsets, weights from OpenCV's table, pixel classes), four shared-memory gathers and
+// the blend per pixel, output tile to shared memory, one TMA store.  No lens arithmetic except for "slow" pixels.
+template <typename G> struct KcGeom { static constexpr int NBUF = G::BW * G::BH * 4 > 16384 ? 2 : 3; };
+constexpr int KC_MAXT = 256;
+
+template <typename SrcT, typename DstT, typename G, bool TSTORE>
+__global__ void __launch_bounds__(KT_THREADS, G::MINB)
+k2_cached_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, K2Args a, int tiles_x,
+                 long long n_items) {
+    constexpr int KT_TW = G::TW, KT_TH = G::TH, KT_BH = G::BH, NBUF = KcGeom<G>::NBUF;
+    constexpr int KT_PX = KT_TW * KT_TH / KT_THREADS, KT_RSTEP = KT_THREADS / KT_TW;
+    constexpr int BW = KtBox<SrcT, G>::BW, BOX_BYTES = KtBox<SrcT, G>::BYTES;
+    constexpr int PK_BYTES = KT_TW * KT_TH * 4, SLOT = BOX_BYTES + PK_BYTES;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full = (uint64_t*)(smem + NBUF * SLOT);
+    int* meta = (int*)(smem + NBUF * SLOT + 64);               // per slot: the item's tile has a box
+    int2* hdrs = (int2*)(smem + NBUF * SLOT + 128);             // box origins of this CTA's tiles (KC_MAXT of them)
+    DstT* otile = (DstT*)(smem + NBUF * SLOT + 128 + KC_MAXT * 8); // [2][TH][TW] when TSTORE
+    const int tid = threadIdx.x;
+    const int c = tid % KT_TW, r0 = tid / KT_TW;
+    const int H = a.H, W = a.W, nf = a.n_frames, ow = a.ow, oh = a.oh;
+    // CTA b owns the tiles b, b + grid, b + 2 grid, ... (all frames of a tile back to back): the CTAs running at the same
+    // time work on neighbouring tiles, whose source boxes overlap (a box is 2.5 x the tile's area) — the overlap is then
+    // served by L2 instead of being read from DRAM again (contiguous ranges per CTA read 2.3 x the algorithmic bytes).
+    const int n_tiles = (int)(n_items / nf);
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (my_tiles == 0) return;
+    const int n_mine = my_tiles * nf;                           // items of this CTA
+    int p_t = 0, p_f = 0, p_k = 0;                              // thread 0: the next item to prefetch = (tile index p_t of this CTA, frame p_f)
+    // the box origins of this CTA's tiles come to shared memory first: thread 0 must not wait for a global load per item
+    for (int t = tid; t < KC_MAXT && t < my_tiles; t += KT_THREADS) hdrs[t] = __ldg(a.chdr + blockIdx.x + t * gridDim.x);
+    __syncthreads();
+
+    auto issue = [&]() {                                        // thread 0: prefetch item lo + p_k = (p_tile, p_f)
+        const int slot = p_k % NBUF;
+        const int p_tile = blockIdx.x + p_t * gridDim.x;
+        const int2 hdr = p_t < KC_MAXT ? hdrs[p_t] : __ldg(a.chdr + p_tile);
+        const bool carries = p_f == 0;
+        const bool box = hdr.x >= 0;
+        meta[slot] = box ? 1 : 0;
+        if (box || carries) {
+            uint8_t* base = smem + slot * SLOT;
+            mbar_expect_tx(&full[slot], (box ? BOX_BYTES : 0) + (carries ? PK_BYTES : 0));
+            if (box) tma_load_3d(base, &tm_src, &full[slot], hdr.x, hdr.y, p_f);
+            if (carries) bulk_load_1d(base + BOX_BYTES, a.cpack + (size_t)p_tile * (KT_TW * KT_TH), PK_BYTES, &full[slot]);
+        }
+        ++p_k;
+        if (++p_f == nf) { p_f = 0; ++p_t; }
+    };
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; ++b) mbar_init(&full[b], 1);
+        mbar_init_fence();
+        for (int k = 0; k < NBUF && k < n_mine; ++k) issue();
+    }
+    __syncthreads();
+
+    int so[KT_PX];
+    Weights<SrcT> wt[KT_PX];
+    unsigned fast = 0, slow = 0, outm = 0, phases = 0;
+    int tx0 = 0, ty0 = 0;
+    const DstT bout = (DstT)border_cast<SrcT>(a.border);
+    const int src_stride = H * W, dst_stride = oh * ow;
+
+    // "slow" pixels (window on the frame rim, or a tile the box does not cover): coordinates recomputed from the lens, per-
+    // neighbour border handling from global memory — a fraction of a percent of the pixels
+    auto slow_pixel = [&](const SrcT* src, int j) -> DstT {
+        float mx, my;
+        undistort_map(a.lens, tx0 + c + a.x0, ty0 + r0 + j * KT_RSTEP + a.y0, mx, my);
+        const FixedCoord fc = fixed_coord_fast(mx, my);
+        Weights<SrcT> w;
+        w.set(fc);
+        return remap_rim<SrcT, DstT>(src, H, W, fc.ix, fc.iy, w, border_cast<SrcT>(a.border));
+    };
+
+    int tile = blockIdx.x, f = 0, slot = 0;
+#pragma unroll 1
+    for (int k = 0; k < n_mine; ++k) {
+        const bool carries = f == 0;
+        const bool have_box = meta[slot] != 0;
+        const uint8_t* base = smem + slot * SLOT;
+        if (have_box || carries) {
+            mbar_wait(&full[slot], (phases >> slot) & 1u);
+            phases ^= 1u << slot;
+        }
+        if (carries) {
+            // a new tile: unpack its coordinates
+            const int tyi = tile / tiles_x;
+            tx0 = (tile - tyi * tiles_x) * KT_TW;
+            ty0 = tyi * KT_TH;
+            const unsigned* pk = (const unsigned*)(base + BOX_BYTES) + tid;
+            const bool col_live = tx0 + c < ow;
+            fast = slow = outm = 0;
+#pragma unroll
+            for (int j = 0; j < KT_PX; ++j) {
+                const unsigned w = pk[j * KT_THREADS];
+                const bool live = col_live && ty0 + r0 + j * KT_RSTEP < oh;
+                so[j] = (w & (KP_OUTSIDE | KP_SLOW)) ? 0 : (int)(w & 0x3fffu);
+                wt[j].lookup((w >> 14) & 1023u, a.wtab);
+                if (live) {
+                    if (w & KP_OUTSIDE) outm |= 1u << j;
+                    else if (w & KP_SLOW) slow |= 1u << j;
+                    else fast |= 1u << j;
+                }
+            }
+        }
+        const SrcT* src = (const SrcT*)a.src + (size_t)f * src_stride;
+        if (TSTORE) {
+            DstT* ot = otile + (k & 1) * (KT_TW * KT_TH) + r0 * KT_TW + c;
+            if (have_box) {
+                const SrcT* box = (const SrcT*)base;
+#pragma unroll
+                for (int j = 0; j < KT_PX; ++j) {
+                    const SrcT* p = box + so[j];
+                    const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                    sts_if(ot + j * KT_RSTEP * KT_TW, r, fast & (1u << j));
+                }
+            }
+            if (outm) {
+#pragma unroll
+                for (int j = 0; j < KT_PX; ++j)
+                    if (outm & (1u << j)) ot[j * KT_RSTEP * KT_TW] = bout;
+            }
+            if (slow) {
+#pragma unroll 1
+                for (int j = 0; j < KT_PX; ++j)
+                    if (slow & (1u << j)) ot[j * KT_RSTEP * KT_TW] = slow_pixel(src, j);
+            }
+            fence_proxy_async_smem();                  // generic-proxy writes of the tile -> visible to the TMA store
+            if (tid == 0) tma_store_wait_read<0>();    // the previous store has read its tile: the other buffer is free again
+            __syncthreads();                           // tile complete; everyone is done with this slot
+            if (tid == 0) {
+                tma_store_3d(&tm_dst, otile + (k & 1) * (KT_TW * KT_TH), tx0, ty0, f);
+                tma_store_commit();
+                if (p_k < n_mine) issue();
+            }
+        } else {
+            DstT* dst = (DstT*)a.dst + (size_t)f * dst_stride + ((ty0 + r0) * ow + tx0 + c);
+            const int dstep = KT_RSTEP * ow;
+            if (have_box) {
+                const SrcT* box = (const SrcT*)base;
+#pragma unroll
+                for (int j = 0; j < KT_PX; ++j) {
+                    const SrcT* p = box + so[j];
+                    const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                    st_if(dst + j * dstep, r, fast & (1u << j));
+                }
+            }
+            if (outm) {
+#pragma unroll
+                for (int j = 0; j < KT_PX; ++j)
+                    if (outm & (1u << j)) dst[j * dstep] = bout;
+            }
+            if (slow) {
+#pragma unroll 1
+                for (int j = 0; j < KT_PX; ++j)
+                    if (slow & (1u << j)) dst[j * dstep] = slow_pixel(src, j);
+            }
+            __syncthreads();                           // everyone is done with this slot
+            if (tid == 0 && p_k < n_mine) issue();
+        }
+        if (++f == nf) { f = 0; tile += gridDim.x; }
+        if (++slot == NBUF) slot = 0;
+    }
+    if (TSTORE && tid == 0) tma_store_wait_read<0>();
+}
+
+template <typename SrcT, typename DstT, typename G, bool TSTORE>
+static cudaError_t launch_cached_g(const K2Args& a, cudaStream_t st) {
+    CUtensorMap tm, td;
+    if (!make_tensor_map(&tm, kt_dtype<SrcT>(), sizeof(SrcT), a.src, a.W, a.H, a.n_frames, KtBox<SrcT, G>::BW, G::BH)) return cudaErrorInvalidValue;
+    td = tm;
+    if (TSTORE && !make_tensor_map(&td, kt_dtype<DstT>(), sizeof(DstT), a.dst, a.ow, a.oh, a.n_frames, G::TW, G::TH)) return cudaErrorInvalidValue;
+    const int tiles_x = (a.ow + G::TW - 1) / G::TW, tiles_y = (a.oh + G::TH - 1) / G::TH;
+    const long long n_items = (long long)tiles_x * tiles_y * a.n_frames;
+    if (n_items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    constexpr int SMEM = KcGeom<G>::NBUF * (KtBox<SrcT, G>::BYTES + G::TW * G::TH * 4) + 128 + KC_MAXT * 8 + (TSTORE ? 2 * G::TW * G::TH * (int)sizeof(DstT) : 0);
+    auto kern = k2_cached_kernel<SrcT, DstT, G, TSTORE>;
+    cudaError_t e = cudaSuccess;
+    const int per_sm = blocks_per_sm_cached((const void*)kern, KT_THREADS, SMEM, &e);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)(a.sm_count > 0 ? a.sm_count : 148) * per_sm;
+    if (grid > (long long)tiles_x * tiles_y) grid = (long long)tiles_x * tiles_y;
+    kern<<<(unsigned)grid, KT_THREADS, SMEM, st>>>(tm, td, a, tiles_x, n_items);
+    return cudaGetLastError();
+}
+
 static bool k2_tiled_eligible(const K2Args& a, int src_dtype, int dst_dtype) {
     const bool pair = (src_dtype == DT_F32 && (dst_dtype == DT_F32 || dst_dtype == DT_F64)) || (src_dtype == DT_U16 && dst_dtype == DT_U16) ||
                       (src_dtype == DT_U8 && dst_dtype == DT_U8);
@@ -472,11 +750,6 @@ static bool k2_tiled_eligible(const K2Args& a, int src_dtype, int dst_dtype) {
     if (a.W < 2 || a.H < 2) return false;
     if (((size_t)a.W * dtype_size(src_dtype)) % 16 || ((uintptr_t)a.src) % 16) return false;
     return tensor_map_encoder() != nullptr;
-}
-
-template <typename T> static CUtensorMapDataType kt_dtype() {
-    return sizeof(T) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
-         : sizeof(T) == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
 }
 
 template <typename SrcT, typename DstT, typename G, bool TSTORE>
@@ -488,9 +761,11 @@ static cudaError_t launch_tiled_g(const K2Args& a, cudaStream_t st) {
     dim3 grid((a.ow + G::TW - 1) / G::TW, (a.oh + G::TH - 1) / G::TH);
     constexpr int SMEM = kt_smem<SrcT, DstT, G, TSTORE>();
     void (*kern)(const CUtensorMap, const CUtensorMap, K2Args);
-    if (a.mapx) kern = k2_tiled_kernel<SrcT, DstT, 0, G, TSTORE>;
-    else if (a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0) kern = k2_tiled_kernel<SrcT, DstT, 2, G, TSTORE>;
-    else kern = k2_tiled_kernel<SrcT, DstT, 1, G, TSTORE>;
+    const bool sep = a.lens.affine && a.lens.ir[1] == 0.0 && a.lens.ir[3] == 0.0;
+    if (a.cpack && !a.mapx) return launch_cached_g<SrcT, DstT, G, TSTORE>(a, st);
+    if (a.mapx) kern = k2_tiled_kernel<SrcT, DstT, 0, G, TSTORE, 0>;
+    else if (a.cpack_w) kern = sep ? k2_tiled_kernel<SrcT, DstT, 2, G, TSTORE, 1> : k2_tiled_kernel<SrcT, DstT, 1, G, TSTORE, 1>;
+    else kern = sep ? k2_tiled_kernel<SrcT, DstT, 2, G, TSTORE, 0> : k2_tiled_kernel<SrcT, DstT, 1, G, TSTORE, 0>;
     if (SMEM > 48 * 1024) {
         cudaError_t e = cudaSuccess;
         blocks_per_sm_cached((const void*)kern, KT_THREADS, SMEM, &e);       // opt-in to > 48 KB, once per (device, kernel)
@@ -503,7 +778,11 @@ static cudaError_t launch_tiled_g(const K2Args& a, cudaStream_t st) {
 template <typename SrcT, typename DstT>
 static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
     // the output tile leaves by TMA when the destination qualifies (16-byte aligned rows), else by predicated stores
-    const bool tstore = ((size_t)a.ow * sizeof(DstT)) % 16 == 0 && ((uintptr_t)a.dst) % 16 == 0;
+    // The output tile can leave through shared memory as one TMA store per frame (UTMASTG) when the destination qualifies
+    // (16-byte aligned rows).  Measured on B200 it is SLOWER than the predicated per-pixel stores of the other path (21.0 vs
+    // 20.1 us per 4096x3000 frame in batches: the tile costs an STS per pixel, a proxy fence and a longer barrier per frame,
+    // while the plain stores are already full 128-byte lines per warp), so it is an option (IMGCORR_OPT_K2_TMA_STORE), off by default.
+    const bool tstore = a.tma_store && ((size_t)a.ow * sizeof(DstT)) % 16 == 0 && ((uintptr_t)a.dst) % 16 == 0;
     const int g = a.geometry;
     if (tstore) {
         if (g == 2) return launch_tiled_g<SrcT, DstT, KtG2, true>(a, st);
@@ -515,8 +794,16 @@ static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
     return launch_tiled_g<SrcT, DstT, KtG0, false>(a, st);
 }
 
+// words of the coordinate cache for an output window under geometry g (whole tiles) and the number of tiles
+void k2_cache_size(int g, int ow, int oh, size_t* words, size_t* tiles) {
+    const int TW = g == 2 ? KtG2::TW : 64, TH = 16;
+    const size_t t = (size_t)((ow + TW - 1) / TW) * ((oh + TH - 1) / TH);
+    *tiles = t;
+    *words = t * (size_t)(TW * TH);
+}
+
 // Host: the staged-box geometry a lens needs for an output window — the largest source window (plus margins) over all
-// 64x16 tiles, from the exact map at the tile perimeters' 3 x 3 sample points (the very points the kernel estimates from).
+// 64x16 tiles, from the exact map at the very 3 x 3 sample points the kernel estimates from.
 // 0: 80x32 box, 1: 112x48, 2: 32-wide tiles with a 112x64 box.  Cached per window by the caller (imgcorr_api.cu).
 int k2_pick_geometry(const LensConst& L, int H, int W, int x0, int y0, int ow, int oh) {
     int need_w = 0, need_h = 0;
@@ -564,6 +851,12 @@ static cudaError_t launch_t(const K2Args& a, cudaStream_t st) {
     else if (separable(a.lens)) k2_remap_kernel<SrcT, DstT, 2><<<grid, K2_BX * K2_BY, 0, st>>>(a);
     else k2_remap_kernel<SrcT, DstT, 1><<<grid, K2_BX * K2_BY, 0, st>>>(a);
     return cudaGetLastError();
+}
+
+bool k2_will_tile(const K2Args& a, int src_dtype, int dst_dtype, int variant) {
+    if (a.H > 32767 || a.W > 32767) return false;
+    const bool want_tiles = variant == 2 || (variant == 0 && (src_dtype == DT_F32 || a.n_frames >= 4));
+    return want_tiles && k2_tiled_eligible(a, src_dtype, dst_dtype);
 }
 
 cudaError_t launch_k2(const K2Args& a, int src_dtype, int dst_dtype, int variant, cudaStream_t st, int* launches) {
