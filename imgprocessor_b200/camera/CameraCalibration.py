@@ -478,12 +478,17 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
 
     # ------------------------------------------------------------------ batches of independent frames
     def correct_batch(self, frames, bgImages=None, exposure_time=None, light_spectrum=None, threshold=0.1,
-                      keep_size=True, date=None, out=None, out_dtype=None, verbose=False):
+                      keep_size=True, date=None, out=None, out_dtype=None, verbose=False, devices=None):
         """correct() for n INDEPENDENT frames with one calibration lookup.
 
         ``frames``: numpy [n,H,W] (uint8 / uint16 / float32, host) -> streamed through pinned buffers with
         H2D / kernels / D2H overlapped, result numpy [n,h,w]; or a CUDA torch tensor [n,H,W] -> result stays
-        on the device.  ``out_dtype`` defaults to float32 (pass float64 for the reference's dtype)."""
+        on the device.  ``out_dtype`` defaults to float32 (pass float64 for the reference's dtype).
+
+        ``devices``: CUDA device indices for host frames, e.g. ``range(8)``: the batch is split contiguously over them
+        (sharding.shard_range), each device gets its own context with the calibration uploaded once and its own host
+        thread driving the pinned H2D / kernels / D2H pipeline (the C ABI calls release the GIL); the shards land in one
+        output array.  No collective is involved: frames are independent."""
         import contextlib
         import io
         tt = _engine.torch()
@@ -495,7 +500,16 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         s = self.coeffs['shape']
         if s is not None and tuple(s[:2]) != (H, W):
             raise Exception('array shapes are different: stored(%s), given(%s)' % (s, (H, W)))
-        dev_index = frames.device.index if is_tensor else None
+        if devices is not None:
+            devices = [int(d) for d in devices]
+            if is_tensor:
+                raise ValueError('devices= shards HOST frames; a CUDA tensor is processed on its own device')
+            if not devices:
+                raise ValueError('devices is empty')
+            if len(devices) > 1:
+                return self._correct_batch_multi(frames, devices, bgImages, exposure_time, light_spectrum, threshold,
+                                                 keep_size, date, out, out_dtype, verbose)
+        dev_index = frames.device.index if is_tensor else (devices[0] if devices else None)
         eng = _engine.get_engine(H, W, dev_index)
         sink = contextlib.nullcontext() if verbose else contextlib.redirect_stdout(io.StringIO())
         with sink:
@@ -525,3 +539,77 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
             frames = frames.astype(np.float32)
         return eng.correct_host(frames, out=out, threshold=thr, ksize=3, flags=flags, use_lens=bool(lens),
                                 window=window, out_dtype=out_dtype or np.float32)
+
+    def _correct_batch_multi(self, frames, devices, bgImages, exposure_time, light_spectrum, threshold, keep_size, date,
+                             out, out_dtype, verbose):
+        """host frames [n,H,W] split over several devices of this process: one engine + one host thread per device"""
+        import contextlib
+        import io
+        import threading
+        from .. import sharding
+        n, H, W = frames.shape
+        be = frames.dtype.kind == 'u' and frames.dtype.itemsize == 2 and frames.dtype.byteorder == '>'
+        if not be and (frames.dtype.type not in (np.uint8, np.uint16, np.float32) or not frames.dtype.isnative):
+            frames = frames.astype(np.float32)
+        engines, own = [], []
+        sink = contextlib.nullcontext() if verbose else contextlib.redirect_stdout(io.StringIO())
+        lens = None
+        try:
+            with sink:
+                for d in devices:
+                    if d in [e.device_index for e in engines]:
+                        e = _engine.Engine(H, W, d)           # the same device twice: a second context (closed below)
+                        own.append(e)
+                    else:
+                        e = _engine.get_engine(H, W, d)
+                    engines.append(e)
+                flags = 0
+                for i, e in enumerate(engines):               # calibration goes to every device once
+                    with contextlib.nullcontext() if (verbose and i == 0) else contextlib.redirect_stdout(io.StringIO()):
+                        flags = self._configure_engine(e, (H, W), bgImages, exposure_time, light_spectrum, date)
+                try:
+                    lens = self.getLens(light_spectrum, date['lens'])
+                    if lens:
+                        lens._lens_setup(W, H)
+                        for e in engines:
+                            e.set_lens(lens.coeffs['cameraMatrix'], lens.coeffs['distortionCoeffs'], lens._new_camera_matrix)
+                except _lib.ImgcorrError:
+                    raise
+                except Exception as errm:
+                    print('Error: %s' % errm)
+                    lens = None
+            if threshold > 0:
+                flags |= _lib.DO_NAN_TO_NUM
+            window = tuple(int(v) for v in lens.roi) if (lens and not keep_size) else None
+            oh, ow = (window[3], window[2]) if window else (H, W)
+            odt = np.dtype(out_dtype or np.float32)
+            if out is None:
+                out = np.empty((n, oh, ow), dtype=odt)
+            if out.shape != (n, oh, ow) or not out.flags.c_contiguous:
+                raise ValueError('out must be C-contiguous of shape %s' % ((n, oh, ow),))
+            thr = threshold if threshold > 0 else 0.0
+            errors = [None] * len(engines)
+
+            def work(i):
+                lo, hi = sharding.shard_range(n, len(engines), i)
+                if hi <= lo:
+                    return
+                try:
+                    engines[i].correct_host(frames[lo:hi], out=out[lo:hi], threshold=thr, ksize=3, flags=flags,
+                                            use_lens=bool(lens), window=window, out_dtype=out.dtype)
+                except BaseException as e:                    # noqa: BLE001 - re-raised in the caller's thread
+                    errors[i] = e
+
+            threads = [threading.Thread(target=work, args=(i,)) for i in range(1, len(engines))]
+            for t in threads:
+                t.start()
+            work(0)
+            for t in threads:
+                t.join()
+            for e in errors:
+                if e is not None:
+                    raise e
+            return out
+        finally:
+            for e in own:
+                e.close()

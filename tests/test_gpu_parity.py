@@ -704,6 +704,60 @@ def test_correct_batch_device_and_host(ip):
     assert r is pin_out and np.array_equal(pin_out.astype(np.float64), single[:, y:y + h, x:x + w])
 
 
+@pytest.mark.parametrize('ndev', [2, 3])
+def test_correct_batch_sharded_over_devices(ip, ndev):
+    """CameraCalibration.correct_batch(frames, devices=...): host frames split contiguously over several contexts, one host
+    thread each, results in one output array — equal to the one-device result.  With fewer physical GPUs than requested the
+    same device is used twice (a second context), which exercises the sharding / threading logic on a one-GPU box; with
+    >= 2 GPUs the shards really run on different devices (contexts, calibration upload, attribute caches per device)."""
+    H, W, n = 96, 128, 11
+    g = load_golden('correct_u16_keep1')
+    cal = _cal(ip, g)
+    frames = np.stack([synth.scene(H, W, 70 + i, np.uint16) for i in range(n)])
+    one = cal.correct_batch(frames, threshold=0.1)
+    have = torch.cuda.device_count()
+    devices = [i % have for i in range(ndev)]
+    got = cal.correct_batch(frames, threshold=0.1, devices=devices)
+    assert got.dtype == np.float32 and np.array_equal(got, one)
+    l = cal.getLens(None, None)
+    l.getUndistortRectifyMap(W, H)
+    x, y, w, h = (int(v) for v in l.roi)
+    from imgprocessor_b200.engine import pinned_empty
+    pin_out = pinned_empty((n, h, w), np.float64)
+    r = cal.correct_batch(frames, threshold=0.1, keep_size=False, out=pin_out, out_dtype=np.float64, devices=devices)
+    assert r is pin_out and np.array_equal(pin_out, one[:, y:y + h, x:x + w].astype(np.float64))
+    assert np.array_equal(cal.correct_batch(frames[:1], threshold=0.1, devices=devices), one[:1])     # fewer frames than devices
+    assert np.array_equal(cal.correct_batch(frames, threshold=0.1, devices=[0]), one)
+    with pytest.raises(ValueError):
+        cal.correct_batch(_dev(frames), devices=devices)
+
+
+def test_two_contexts_on_two_devices_in_one_process(ip):
+    """the shared-memory opt-in of the TMA kernels (cudaFuncSetAttribute) is per device: a context on a second device of the
+    same process must launch them as well (the attribute used to be cached process-wide)"""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two CUDA devices')
+    H, W = 96, 128
+    raw, dark, flat = _case(H, W, 5)
+    outs = []
+    for dev in (0, 1):
+        e = ip.engine_mod.Engine(H, W, dev)
+        e.set_dark(dark)
+        e.set_flat(flat)
+        p = synth.lens_moderate(H, W)
+        import cv2
+        K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+        P, _ = cv2.getOptimalNewCameraMatrix(K, d, (W, H), 1, (W, H))
+        e.set_lens(K, d, P)
+        frames = torch.from_numpy(np.stack([raw] * 5)).to('cuda:%d' % dev)
+        with torch.cuda.device(dev):
+            outs.append(e.correct_batch(frames, 0.1, 3).cpu().numpy())
+            out5, _ = e.pointwise_median(frames, 0.1, 5)
+            outs.append(out5.cpu().numpy())
+        e.close()
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[1], outs[3])
+
+
 def test_correct_host_chunks_small_frames(ip):
     """small frames go through the host pipeline in chunks of up to 16 per ring slot: more chunks than slots, a ragged last
     chunk, pinned and pageable buffers — same output as the device-resident chain"""

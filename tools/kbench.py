@@ -59,21 +59,13 @@ def main():
                      'GBps_median': round(bytes_px * px / med * 1e-3, 1), 'Gpx_s': round(px / med * 1e-3, 2)}
         print(name, res[name], flush=True)
 
-    for variant, nm in ((1, 'k1_generic'), (2, 'k1_tma'), (3, 'k1_stream'), (4, 'k1_stream2')):
+    for variant, nm in ((1, 'k1_generic'), (2, 'k1_tma'), (3, 'k1_stream')):
         e.set_option(_lib.OPT_K1_VARIANT, variant)
         try:
             med, best = timeit(lambda i: e.pointwise_median(raw[i % n], 0.1, a.ksize, out=mid[i % n:i % n + 1]), a.iters)
             rep(nm, med, best, rb + 12)
         except Exception as ex:
             print(nm, 'failed:', ex)
-    for seg in ():
-        e.set_option(_lib.OPT_K1_VARIANT, 4)
-        e.set_option(_lib.OPT_K1_SEG_ROWS, seg)
-        try:
-            med, best = timeit(lambda i: e.pointwise_median(raw[i % n], 0.1, a.ksize, out=mid[i % n:i % n + 1]), a.iters)
-            rep('k1_stream2_seg%d' % seg, med, best, rb + 12)
-        except Exception as ex:
-            print('stream seg', seg, 'failed:', ex)
     e.set_option(_lib.OPT_K1_SEG_ROWS, 0)
     e.set_option(_lib.OPT_K1_VARIANT, 0)
     med, best = timeit(lambda i: e.pointwise_median(raw[i % n], 0.0, 0, flags=3, out=mid[i % n:i % n + 1]), a.iters)
