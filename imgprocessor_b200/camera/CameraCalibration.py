@@ -19,6 +19,7 @@ import numpy as np
 from .. import _lib
 from .. import engine as _engine
 from ..imgIO import imread
+from . import NoiseLevelFunction as _nlf
 from .LensDistortion import LensDistortion
 
 DATE_FORMAT = "%d %b %y - %H:%M"   # e.g. '30 Nov 15 - 13:20'
@@ -314,7 +315,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
             if type(bgImages) in (list, tuple) or (isinstance(bgImages, np.ndarray) and bgImages.ndim == 3):
                 if len(bgImages) > 1:
                     # several background images: STE-free average (:488-494), kernel K4
-                    bg = self._ste_average(bgImages, self._nlf_coeff(None))
+                    bg = self._ste_average(bgImages, self.noise_level_function)       # whatever it is, None included (:490-494)
                 else:
                     bg = imread(bgImages[0])
             else:
@@ -366,26 +367,23 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         return flags
 
     # ------------------------------------------------------------------ single-time-effect removal (K4)
-    def _nlf_coeff(self, date):
-        """(minY, ax, ay) of NoiseLevelFunction.boundedFunction: the 'noise' calibration entry (:392-397), or what an
-        earlier call stored.  The reference otherwise ESTIMATES a noise level function from the images (oneImageNLF,
-        a host-side histogram fit through the absent fancytools) — not reproduced."""
+    def _calibrated_nlf(self, date):
+        """the 'noise' calibration entry becomes the noise level function on first use (:392-397); None if there is neither
+        an entry nor a function from an earlier call — SingleTimeEffectDetection then estimates one from the images"""
         if self.noise_level_function is None:
             n = self.coeffs['noise']
             if len(n):
                 coeff = tuple(float(v) for v in _getFromDate(n, date)[2])
                 self.noise_level_function = _BoundedNLF(*coeff)
-        nlf = self.noise_level_function
-        if nlf is None:
-            raise NotImplementedError('single-time-effect removal without a noise calibration needs oneImageNLF '
-                                      '(host-side estimation, not on the GPU path); call addNoise((minY, ax, ay)) first')
-        if not isinstance(nlf, _BoundedNLF):
-            raise NotImplementedError('an arbitrary Python noise_level_function cannot run on the GPU; use '
-                                      'addNoise((minY, ax, ay)) (NoiseLevelFunction.boundedFunction parameters)')
-        return nlf.coeff
+        return self.noise_level_function
 
-    def _ste_average(self, images, coeff, n_std=4):
-        """SingleTimeEffectDetection(images, nStd=4, noise_level_function=nlf).noSTE (:401-403, 491-494) -> float64"""
+    def _ste_average(self, images, nlf, n_std=4, keep_estimate=False):
+        """SingleTimeEffectDetection(images, nStd=4, noise_level_function=nlf).noSTE (:401-403, 491-494) -> float64.
+        ``nlf`` None: the function is estimated from min(images[0], images[1]) like the reference does
+        (SingleTimeEffectDetection.py:43-45 -> NoiseLevelFunction.oneImageNLF) and, in the main branch of correct(), kept
+        for later calls (:405-406).  boundedFunction-shaped functions are evaluated per pixel inside kernel K4; any other
+        callable (the polynomial fallback of the estimate, a user's own function) is evaluated here on
+        min(images[0], images[1]) and handed to K4 as a threshold map."""
         frames = [imread(i, 'gray') for i in images]
         if any(f.ndim != 2 or f.shape != frames[0].shape for f in frames):
             raise ValueError('single-time-effect removal needs 2-D frames of one shape')
@@ -393,9 +391,24 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         if dt.type not in (np.uint8, np.uint16, np.float32, np.float64):
             dt = np.dtype(np.float64)
         stack = np.stack([np.asarray(f, dtype=dt.newbyteorder('=')) for f in frames])
+        first = None
+        if nlf is None:
+            first = np.min((stack[0].astype(np.float64), stack[1]), axis=0)
+            nlf = _nlf.oneImageNLF(first)[0]
+            if keep_estimate:
+                self.noise_level_function = nlf
+        params = getattr(nlf, 'coeff', None)
+        if params is None:
+            params = getattr(nlf, 'params', None)
         eng = _engine.get_engine(*stack.shape[1:])
         tt = _engine.torch()
-        return _engine.to_numpy(eng.ste_average(tt.from_numpy(stack).to(eng.device), coeff, n_std))
+        dev = tt.from_numpy(stack).to(eng.device)
+        if params is not None:
+            return _engine.to_numpy(eng.ste_average(dev, params, n_std))
+        if first is None:
+            first = np.min((stack[0].astype(np.float64), stack[1]), axis=0)
+        thr = np.broadcast_to(np.asarray(nlf(first), dtype=np.float64) * n_std, first.shape)
+        return _engine.to_numpy(eng.ste_average(dev, threshold=thr))
 
     # ------------------------------------------------------------------ THE hot path
     def correct(self, images, bgImages=None, exposure_time=None, light_spectrum=None, threshold=0.1, keep_size=True,
@@ -403,7 +416,8 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
         """Correct one frame: dark current, flat field, 3x3 median-threshold artefact removal, lens
         distortion.  Same arguments and return value (a new float64 array; the input is never modified)
         as the reference.  Several exposures of one scene (list / 3-D array) are first merged into one
-        single-time-effect-free average (kernel K4; needs a 'noise' calibration entry).  Not supported on the GPU
+        single-time-effect-free average (kernel K4; the noise level function comes from the 'noise' calibration or is
+        estimated from the exposures as in the reference).  Not supported on the GPU
         path: ``denoise``; ``deblur`` is reported and skipped like any other failing stage."""
         print('CORRECT CAMERA ...')
         date, light_spectrum = self._normalise_args(date, light_spectrum)
@@ -412,7 +426,7 @@ if shapes are transposed, execute self.transpose() once """ % (s, array.shape))
             if len(images) > 1:
                 # several exposures of the same scene: one STE-free average (:390-406), kernel K4
                 print('... remove single-time-effects from images ')
-                images = self._ste_average(images, self._nlf_coeff(date['noise']))
+                images = self._ste_average(images, self._calibrated_nlf(date['noise']), keep_estimate=True)
             else:
                 images = images[0]
         image = imread(images)

@@ -626,9 +626,26 @@ extern "C" IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* c, const void* src_de
 }
 
 // ---- K4 -------------------------------------------------------------------------------------
+static int ste_average_impl(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                            uint8_t* mask_dev, const double nlf[3], double n_std, const double* thr_dev, void* stream);
+
 extern "C" IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
                                    uint8_t* mask_dev, const double nlf[3], double n_std, void* stream) {
     GUARD(c);
+    if (!nlf) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    return ste_average_impl(c, frames_dev, dtype, n_frames, avg_dev, mask_dev, nlf, n_std, nullptr, stream);
+}
+
+extern "C" IMGCORR_API int imgcorr_ste_average_thr(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                                       uint8_t* mask_dev, const double* threshold_dev, void* stream) {
+    GUARD(c);
+    if (!threshold_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    const double none[3] = {0.0, 0.0, 0.0};
+    return ste_average_impl(c, frames_dev, dtype, n_frames, avg_dev, mask_dev, none, 1.0, threshold_dev, stream);
+}
+
+static int ste_average_impl(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                            uint8_t* mask_dev, const double nlf[3], double n_std, const double* thr_dev, void* stream) {
     if (!frames_dev || !avg_dev || !nlf) return fail(IMGCORR_ERR_INVALID, "null pointer");
     if (dtype < DT_U8 || dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
     if (n_frames < 2) return fail(IMGCORR_ERR_INVALID, "single-time-effect removal needs at least 2 images (got %d)", n_frames);
@@ -646,6 +663,7 @@ extern "C" IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* c, const void* frame
     a.H = c->H;
     a.W = c->W;
     a.thr = c->ste_thr;
+    a.thr_in = thr_dev;
     a.n = c->ste_n;
     a.mask = mask_dev;
     a.sc.minY = nlf[0];

@@ -96,6 +96,7 @@ struct K4Args {
     const void* img2;       // FIRST launch only: images[1]; null for the following images
     const double* avg_in;   // [H][W] running average (noSTE) before this image (unused by the FIRST launch)
     double* avg_out;        // [H][W] running average after it (a different buffer: neighbouring tiles read avg_in)
+    const double* thr_in;   // FIRST launch: caller-supplied threshold map (already times nStd) instead of the boundedFunction model, or null
     double* thr;            // [H][W] threshold = nlf(avg after the first update) * nStd
     int* n;                 // [H][W] number of values averaged per pixel
     uint8_t* mask;          // [H][W] accumulated STE mask (save_ste_indices) or null

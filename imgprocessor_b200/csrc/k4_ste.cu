@@ -31,7 +31,7 @@ struct SteLoad {
             // np.min / np.max over the pair (:40, :48); a NaN in either propagates as numpy's reduction does
             avg = (p != p || q != q) ? (p + q) : (p < q ? p : q);
             img = (p != p || q != q) ? (p + q) : (p < q ? q : p);
-            thr = ste_threshold(a.sc, avg);
+            thr = a.thr_in ? __ldg(a.thr_in + i) : ste_threshold(a.sc, avg);
         } else {
             img = (double)__ldg((const T*)a.img + i);
             avg = __ldg(a.avg_in + i);

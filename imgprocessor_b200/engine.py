@@ -295,20 +295,45 @@ class Engine(object):
             int(bool(inverse_map)), float(border_value), self._stream()))
         return out[0] if squeeze else out
 
-    def ste_average(self, frames, nlf, n_std=4.0, want_mask=False):
+    def ste_average(self, frames, nlf=None, n_std=4.0, want_mask=False, threshold=None):
         """K4: SingleTimeEffectDetection(frames, nStd=n_std, noise_level_function=boundedFunction(., *nlf)).noSTE
         for device frames [n,H,W] (n >= 2) -> float64 [H,W] (and the accumulated STE mask if asked)
-        (features/SingleTimeEffectDetection.py:23-75)."""
+        (features/SingleTimeEffectDetection.py:23-75).  ``threshold``: a float64 [H,W] map
+        noise_level_function(min(frames[0], frames[1])) * nStd for noise level functions other than boundedFunction."""
         tt = torch()
         frames = self._frames(frames)
         n = frames.shape[0]
         avg = tt.empty((self.H, self.W), dtype=tt.float64, device=self.device)
         mask = tt.empty((self.H, self.W), dtype=tt.uint8, device=self.device) if want_mask else None
-        coeff = (ctypes.c_double * 3)(*[float(v) for v in nlf])
-        _lib.check(self.lib.imgcorr_ste_average(
-            self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, ctypes.c_void_p(avg.data_ptr()),
-            ctypes.c_void_p(mask.data_ptr()) if want_mask else None, coeff, float(n_std), self._stream()))
+        mp = ctypes.c_void_p(mask.data_ptr()) if want_mask else None
+        if threshold is not None:
+            thr = threshold if isinstance(threshold, tt.Tensor) else tt.from_numpy(np.ascontiguousarray(threshold, dtype=np.float64))
+            thr = thr.to(device=self.device, dtype=tt.float64).contiguous()
+            if tuple(thr.shape) != (self.H, self.W):
+                raise ValueError('threshold map shape %s != frame shape %s' % (tuple(thr.shape), (self.H, self.W)))
+            _lib.check(self.lib.imgcorr_ste_average_thr(
+                self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, ctypes.c_void_p(avg.data_ptr()),
+                mp, ctypes.c_void_p(thr.data_ptr()), self._stream()))
+        else:
+            if nlf is None:
+                raise ValueError('ste_average needs the boundedFunction parameters (nlf) or a threshold map')
+            coeff = (ctypes.c_double * 3)(*[float(v) for v in nlf])
+            _lib.check(self.lib.imgcorr_ste_average(
+                self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, ctypes.c_void_p(avg.data_ptr()),
+                mp, coeff, float(n_std), self._stream()))
         return (avg, mask.bool()) if want_mask else avg
+
+    def median3x3(self, img):
+        """scipy.ndimage.median_filter(img, 3) (mode='reflect') of a host float64 / float32 image through K1: a median-threshold
+        whose threshold is so small that every pixel differing from its median is replaced by it (and a pixel equal to
+        its median already is the median).  Used by the noise-level-function estimation (camera/NoiseLevelFunction.py)."""
+        tt = torch()
+        a = np.ascontiguousarray(img)
+        if a.dtype not in (np.float64, np.float32):
+            a = a.astype(np.float64)
+        dev = tt.from_numpy(a).to(self.device)
+        out, _ = self.pointwise_median(dev, 1e-300, 3, flags=0, out_dtype=dev.dtype)
+        return to_numpy(out)
 
     def undistort_maps(self):
         tt = torch()

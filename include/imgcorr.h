@@ -191,6 +191,12 @@ IMGCORR_API int imgcorr_divide_f64(imgcorr_ctx* ctx, const void* src_dev, int sr
  * MaskedMovingAverage (absent from the reference tree: that ingredient's parity is unpinned, see oracle/ste.py). */
 IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
                         uint8_t* mask_dev, const double nlf[3], double n_std, void* stream);
+/* The same with a caller-supplied threshold map  threshold_dev[H][W] = noise_level_function(min(images[0], images[1])) * nStd
+ * (float64) for noise level functions that are not boundedFunction: the one correct() ESTIMATES when no 'noise' calibration
+ * exists may be a polynomial (oneImageNLF -> smooth, camera/NoiseLevelFunction.py:132-159), and a user may have assigned any
+ * Python callable to CameraCalibration.noise_level_function. */
+IMGCORR_API int imgcorr_ste_average_thr(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
+                            uint8_t* mask_dev, const double* threshold_dev, void* stream);
 
 /* ---- self-test ---------------------------------------------------------------------------------------
  * K1 and K4 divide in float64 with a shortened Newton sequence (MUFU.RCP64H seed, one refinement, residual correction:

@@ -278,8 +278,64 @@ def ste():
          bf_y=NoiseLevelFunction.boundedFunction(xs, *nlf), **out)
 
 
+def ste_nlf():
+    """SURVEY §8 a11 / f1 without a 'noise' calibration: the reference then ESTIMATES the noise level function from the images
+    (SingleTimeEffectDetection.py:43-45 -> NoiseLevelFunction.oneImageNLF -> calcNLF / _evaluate, unmodified; the restated
+    MaskedMovingAverage injected as in ste())."""
+    ref_shim.install_masked_moving_average()
+    import importlib
+    import imgProcessor.features.SingleTimeEffectDetection as stemod
+    importlib.reload(stemod)
+    from imgProcessor.camera import NoiseLevelFunction
+    import imgProcessor.camera.CameraCalibration as calmod
+    calmod.SingleTimeEffectDetection = stemod.SingleTimeEffectDetection
+    rng = np.random.default_rng(77)
+    H, W = 120, 160
+    base = synth.scene(H, W, seed=9, dtype=np.float64, full_scale=4000.0, hot_dead=False)
+    nlf = (6.0, 20.0, 0.9)
+    frames = []
+    for i in range(4):
+        f = base + rng.normal(0, 1, (H, W)) * NoiseLevelFunction.boundedFunction(base, *nlf)
+        for k in range(8):
+            y, x = rng.integers(2, H - 3), rng.integers(2, W - 3)
+            f[y:y + rng.integers(1, 4), x:x + rng.integers(1, 4)] += rng.uniform(300, 3000)
+        frames.append(np.clip(np.rint(f), 0, 65535).astype(np.uint16))
+    frames = np.stack(frames)
+    out = {}
+    avg0 = np.min((frames[0].astype(np.float64), frames[1]), axis=0)
+    x, y, w, signal = NoiseLevelFunction.calcNLF(avg0)
+    params, fn, valid = NoiseLevelFunction._evaluate(x, y, w)
+    out.update(avg0=avg0, nlf_x=x, nlf_y=y, nlf_w=w, nlf_signal=signal, nlf_params=params, nlf_valid=valid,
+               nlf_curve_x=np.linspace(0, 4500, 91), nlf_curve=fn(np.linspace(0, 4500, 91)))
+    x2, y2, w2, s2 = NoiseLevelFunction.calcNLF(frames[0], frames[1])                 # two-image estimate
+    out.update(nlf2_x=x2, nlf2_y=y2, nlf2_w=w2, nlf2_signal=s2)
+    for n in (2, 4):
+        det = stemod.SingleTimeEffectDetection(list(frames[:n]), nStd=4, save_ste_indices=True)
+        out['noSTE_%d' % n] = det.noSTE
+        out['mask_%d' % n] = det.mask_STE
+    # a noise level function the square-root model cannot describe: the polynomial fallback (smooth)
+    xs = np.linspace(100, 3000, 40)
+    ys = 30.0 + 1e-5 * (xs - 1500.0) ** 2 - 25.0 * (xs > 2500)
+    ws = np.linspace(50, 500, 40)
+    sm = NoiseLevelFunction.smooth(xs, ys, ws)
+    out.update(smooth_x=xs, smooth_y=ys, smooth_w=ws, smooth_eval_x=np.linspace(-100, 3500, 61), smooth_eval=sm(np.linspace(-100, 3500, 61)))
+    dark = synth.dark_map(H, W)
+    flat = synth.flat_map(H, W, p_zero=2e-3)
+    params_l = synth.lens_moderate(H, W)
+    cal = calmod.CameraCalibration()
+    cal.addDarkCurrent(dark)
+    cal.addFlatField(flat)
+    cal.addLens(make_lens(params_l, (H, W)))
+    out['correct_3'], lg = quiet(cal.correct, list(frames[:3]), threshold=0.1)        # no addNoise: NLF estimated, then kept
+    out['correct_3_log'] = np.array(lg)
+    out['correct_3_again'], _ = quiet(cal.correct, list(frames[1:4]), threshold=0.1)  # second call re-uses the kept function
+    save('ste_nlf', frames=frames, dark=dark, flat=flat, K=synth.camera_matrix(params_l), dist=synth.dist_coeffs(params_l), **out)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['perspective']:
+    if sys.argv[1:] == ['ste_nlf']:
+        ste_nlf()
+    elif sys.argv[1:] == ['perspective']:
         perspective()
     elif sys.argv[1:] == ['ste']:
         ste()
@@ -287,3 +343,4 @@ if __name__ == '__main__':
         main()
         perspective()
         ste()
+        ste_nlf()

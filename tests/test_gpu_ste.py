@@ -107,9 +107,6 @@ def test_correct_with_several_exposures():
     cal.addDarkCurrent(g['dark'])
     cal.addFlatField(g['flat'])
     cal.addLens(lens)
-    with pytest.raises(NotImplementedError):                   # no noise calibration: the reference would estimate one
-        with contextlib.redirect_stdout(io.StringIO()):
-            cal.correct(list(fr[:3]))
     cal.addNoise(tuple(g['nlf']))
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
@@ -123,9 +120,64 @@ def test_correct_with_several_exposures():
     cal2 = CameraCalibration()
     cal2.addFlatField(g['flat'])
     cal2.addNoise(tuple(g['nlf']))
+    # the bgImages branch hands self.noise_level_function to the STE detection as it is (:490-494); the golden run set it to
+    # the reference's own lambda — an arbitrary callable here, which goes to K4 as a threshold map
+    from imgprocessor_b200.camera import NoiseLevelFunction as nlfmod
+    nlf = tuple(g['nlf'])
+    cal2.noise_level_function = lambda x: nlfmod.boundedFunction(x, *nlf)
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf):
         out = cal2.correct(fr[0], bgImages=list(g['bgs']), threshold=0.1)
     assert buf.getvalue() == str(g['correct_bg3_log'])
     assert np.array_equal(cal2.temp['bg'], g['correct_bg3_bg'])
     assert np.abs(out - g['correct_bg3']).max() <= 1e-5 * 65535
+
+
+def test_noise_level_function_estimated_when_uncalibrated():
+    """correct([a, b, c]) WITHOUT a 'noise' calibration: the reference estimates the noise level function from the exposures
+    (SingleTimeEffectDetection.py:43-45 -> NoiseLevelFunction.oneImageNLF) and keeps it.  Golden: the unmodified reference
+    (tests/golden/make_golden.py ste_nlf).  The 3x3 median of the estimate runs on the GPU (K1) and must equal scipy's
+    bit for bit; bins, fit parameters, STE-free averages and masks follow bit for bit; the corrected frame within the
+    float32 chain's 1e-5 of full scale."""
+    if not torch.cuda.is_available():
+        pytest.skip('needs a CUDA device')
+    from imgprocessor_b200 import engine
+    from imgprocessor_b200.camera import CameraCalibration, LensDistortion
+    from imgprocessor_b200.camera import NoiseLevelFunction as nlfmod
+    g = load_golden('ste_nlf')
+    fr = g['frames']
+    H, W = fr.shape[1:]
+    e = engine.get_engine(H, W)
+    assert np.array_equal(e.median3x3(g['avg0']), g['nlf_signal'])
+    x, y, w, signal = nlfmod.calcNLF(g['avg0'])
+    filled = g['nlf_w'] > 0
+    assert np.array_equal(w, g['nlf_w']) and np.array_equal(signal, g['nlf_signal'])
+    assert np.array_equal(x[filled], g['nlf_x'][filled]) and np.array_equal(y[filled], g['nlf_y'][filled])
+    x2, y2, w2, s2 = nlfmod.calcNLF(fr[0], fr[1])                     # the two-image estimate
+    f2 = g['nlf2_w'] > 0
+    assert np.array_equal(w2, g['nlf2_w']) and np.array_equal(s2, g['nlf2_signal']) and np.array_equal(y2[f2], g['nlf2_y'][f2])
+    fn, _ = nlfmod.oneImageNLF(g['avg0'])
+    assert np.array_equal(np.asarray(fn.params), g['nlf_params'])
+    assert np.array_equal(fn(g['nlf_curve_x']), g['nlf_curve'])
+    for n in (2, 4):
+        avg, mask = e.ste_average(torch.from_numpy(fr[:n].copy()).cuda(), fn.params, 4.0, want_mask=True)
+        assert np.array_equal(avg.cpu().numpy(), g['noSTE_%d' % n])
+        assert np.array_equal(mask.cpu().numpy(), g['mask_%d' % n])
+        # the same through a threshold map (what a non-boundedFunction callable gets)
+        thr = fn(g['avg0']) * 4.0
+        avg2 = e.ste_average(torch.from_numpy(fr[:n].copy()).cuda(), threshold=thr)
+        assert np.array_equal(avg2.cpu().numpy(), g['noSTE_%d' % n])
+    lens = LensDistortion({'cameraMatrix': g['K'], 'distortionCoeffs': g['dist'], 'shape': (H, W)})
+    cal = CameraCalibration()
+    cal.addDarkCurrent(g['dark'])
+    cal.addFlatField(g['flat'])
+    cal.addLens(lens)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        out = cal.correct(list(fr[:3]), threshold=0.1)
+    assert buf.getvalue() == str(g['correct_3_log'])
+    assert np.abs(out - g['correct_3']).max() <= 1e-5 * 65535
+    assert cal.noise_level_function is not None and np.array_equal(np.asarray(cal.noise_level_function.params), g['nlf_params'])
+    with contextlib.redirect_stdout(io.StringIO()):
+        again = cal.correct(list(fr[1:4]), threshold=0.1)              # re-uses the kept function, as the reference does
+    assert np.abs(again - g['correct_3_again']).max() <= 1e-5 * 65535
