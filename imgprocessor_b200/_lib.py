@@ -46,6 +46,11 @@ SIGNATURES = {
     'imgcorr_divide_f64': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
     'imgcorr_ste_average': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
     'imgcorr_ste_average_thr': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'imgcorr_stack_mean': (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_double, c_int, c_int, c_void_p, c_void_p]),
+    'imgcorr_scale_f64': (c_int, [c_void_p, c_void_p, c_size_t, c_double, c_void_p]),
+    'imgcorr_subsample_f64': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'imgcorr_linear_fit': (c_int, [c_void_p, c_void_p, c_int, c_int, c_size_t, c_void_p, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                   c_void_p]),
     'imgcorr_selftest_division': (c_int, [c_void_p, c_int, ctypes.c_ulonglong, ctypes.POINTER(c_double)]),
     'imgcorr_host_fingerprint': (c_int, [c_void_p, c_size_t, ctypes.POINTER(ctypes.c_ulonglong)]),
     'imgcorr_host_alloc': (c_int, [c_size_t, ctypes.POINTER(c_void_p)]),

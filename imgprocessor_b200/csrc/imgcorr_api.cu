@@ -893,6 +893,68 @@ extern "C" IMGCORR_API int imgcorr_selftest_division(imgcorr_ctx* c, int numerat
     return IMGCORR_OK;
 }
 
+// ---- K5 -------------------------------------------------------------------------------------
+extern "C" IMGCORR_API int imgcorr_stack_mean(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, size_t elems,
+                                  const double* minus_dev, double minus_scalar, int use_scalar, int gray3, double* out_dev, void* stream) {
+    GUARD(c);
+    if (!frames_dev || !out_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (dtype < DT_U8 || dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
+    if (n_frames < 1) return fail(IMGCORR_ERR_INVALID, "n_frames %d", n_frames);
+    if (gray3 && elems % 3) return fail(IMGCORR_ERR_INVALID, "gray conversion needs 3 interleaved channels");
+    int l = 0;
+    cudaError_t e = launch_k5_stack_mean(frames_dev, dtype, n_frames, elems, minus_dev, minus_scalar, use_scalar, gray3, out_dev, c->sm_count,
+                                         (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "stack mean launch");
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_scale_f64(imgcorr_ctx* c, double* data_dev, size_t elems, double divisor, void* stream) {
+    GUARD(c);
+    if (!data_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    int l = 0;
+    cudaError_t e = launch_k5_scale(data_dev, elems, divisor, c->sm_count, (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "scale launch");
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_subsample_f64(imgcorr_ctx* c, const double* src_dev, int height, int width, int step_y, int step_x,
+                                     double* dst_dev, void* stream) {
+    GUARD(c);
+    if (!src_dev || !dst_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (height <= 0 || width <= 0 || step_y <= 0 || step_x <= 0) return fail(IMGCORR_ERR_INVALID, "bad shape / step");
+    int l = 0;
+    cudaError_t e = launch_k5_subsample(src_dev, height, width, step_y, step_x, dst_dev, (cudaStream_t)stream, &l);
+    c->launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "subsample launch");
+    return IMGCORR_OK;
+}
+
+extern "C" IMGCORR_API int imgcorr_linear_fit(imgcorr_ctx* c, const void* frames_dev, int dtype, int n_frames, size_t pixels, const double* x_host,
+                                  double max_intensity, double min_ascent, double* offset_dev, double* ascent_dev, double* rmse_dev,
+                                  void* stream) {
+    GUARD(c);
+    if (!frames_dev || !x_host || !offset_dev || !ascent_dev) return fail(IMGCORR_ERR_INVALID, "null pointer");
+    if (dtype < DT_U8 || dtype > DT_F64) return fail(IMGCORR_ERR_INVALID, "bad dtype %d", dtype);
+    if (n_frames < 2) return fail(IMGCORR_ERR_INVALID, "a line needs at least 2 exposure times (got %d)", n_frames);
+    double mn = x_host[0], mx = x_host[0];
+    for (int k = 1; k < n_frames; ++k) { mn = x_host[k] < mn ? x_host[k] : mn; mx = x_host[k] > mx ? x_host[k] : mx; }
+    double* xs = nullptr;
+    CK(cudaMalloc((void**)&xs, n_frames * sizeof(double)));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(xs, x_host, n_frames * sizeof(double), cudaMemcpyHostToDevice, st);
+    int l = 0;
+    if (e == cudaSuccess)
+        e = launch_k5_linear_fit(frames_dev, dtype, n_frames, pixels, xs, max_intensity, min_ascent, 0.5 * (mn + mx), offset_dev, ascent_dev,
+                                 rmse_dev, c->sm_count, st, &l);
+    c->launches += l;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);       // x_host / xs may go away when this returns
+    cudaFree(xs);
+    if (e != cudaSuccess) return cuda_fail(e, "linear fit");
+    return IMGCORR_OK;
+}
+
 // ---- host-side fingerprint of a calibration array ---------------------------------------------------------
 static unsigned long long fp_chunk(const unsigned char* p, size_t n) {
     // four independent multiply-xor lanes over 8-byte words (the loop is load bound), tail bytes folded in at the end

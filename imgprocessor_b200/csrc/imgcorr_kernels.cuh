@@ -105,6 +105,14 @@ struct K4Args {
 };
 cudaError_t launch_k4(const K4Args& a, int dtype, cudaStream_t stream, int* launches);
 
+// K5: calibration-map producers (k5_producers.cu) -------------------------------------------
+cudaError_t launch_k5_stack_mean(const void* frames, int dtype, int n, size_t elems, const double* minus, double minus_scalar,
+                                 int has_scalar, int gray3, double* out, int sm_count, cudaStream_t stream, int* launches);
+cudaError_t launch_k5_scale(double* data, size_t elems, double divisor, int sm_count, cudaStream_t stream, int* launches);
+cudaError_t launch_k5_subsample(const double* src, int H, int W, int sy, int sx, double* dst, cudaStream_t stream, int* launches);
+cudaError_t launch_k5_linear_fit(const void* frames, int dtype, int n, size_t px, const double* xs_dev, double max_intensity, double min_ascent,
+                                 double x_mid, double* offset, double* ascent, double* rmse, int sm_count, cudaStream_t stream, int* launches);
+
 // device self-test of the float64 division sequence (selftest.cu); dev2 = {mismatches, bits of the worst seed error}
 cudaError_t launch_selftest_division(int nnum, uint64_t seed, unsigned long long* dev2, cudaStream_t stream);
 

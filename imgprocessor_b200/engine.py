@@ -335,6 +335,62 @@ class Engine(object):
         out, _ = self.pointwise_median(dev, 1e-300, 3, flags=0, out_dtype=dev.dtype)
         return to_numpy(out)
 
+    # -- K5: calibration-map producers (frame sizes are free; the engine only supplies the device) -----------
+    def stack_mean(self, frames, minus=None, gray3=False):
+        """imgAverage(frames) [- minus] [-> toGray]: frames = device tensor [n, ...] (any supported dtype; colour frames
+        [n,H,W,3] with gray3) -> float64 tensor of one frame's shape (without the channel axis if gray3)"""
+        tt = torch()
+        frames = frames.contiguous()
+        n = frames.shape[0]
+        elems = int(frames[0].numel())
+        shape = tuple(frames.shape[1:-1]) if gray3 else tuple(frames.shape[1:])
+        out = tt.empty(shape, dtype=tt.float64, device=self.device)
+        mp, ms, use = None, 0.0, 0
+        keep = None
+        if minus is not None:
+            if isinstance(minus, (int, float)):
+                ms, use = float(minus), 1
+            else:
+                keep = (minus if isinstance(minus, tt.Tensor) else tt.from_numpy(np.ascontiguousarray(minus, dtype=np.float64)))
+                keep = keep.to(device=self.device, dtype=tt.float64).contiguous()
+                if keep.numel() != elems:
+                    raise ValueError('background of %d samples for frames of %d' % (keep.numel(), elems))
+                mp = ctypes.c_void_p(keep.data_ptr())
+        _lib.check(self.lib.imgcorr_stack_mean(self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, elems,
+                                               mp, ms, use, int(bool(gray3)), ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def scale_(self, data, divisor):
+        """data /= divisor in place (float64 device tensor)"""
+        _lib.check(self.lib.imgcorr_scale_f64(self._h, ctypes.c_void_p(data.data_ptr()), int(data.numel()), float(divisor), self._stream()))
+        return data
+
+    def subsample(self, img, step_y, step_x):
+        """img[::step_y, ::step_x] of a float64 device image"""
+        tt = torch()
+        h, w = img.shape
+        out = tt.empty(((h + step_y - 1) // step_y, (w + step_x - 1) // step_x), dtype=tt.float64, device=self.device)
+        _lib.check(self.lib.imgcorr_subsample_f64(self._h, ctypes.c_void_p(img.data_ptr()), h, w, int(step_y), int(step_x),
+                                                  ctypes.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def linear_fit(self, frames, x, max_intensity=65535, min_ascent=0.001, want_rmse=True):
+        """per-pixel line frames[k] = offset + ascent * x[k] (getLinearityFunction): device tensor [n,H,W] -> float64 offset,
+        ascent (, rmse)"""
+        tt = torch()
+        frames = frames.contiguous()
+        n = frames.shape[0]
+        px = int(frames[0].numel())
+        xs = (ctypes.c_double * n)(*[float(v) for v in x])
+        offset = tt.empty(tuple(frames.shape[1:]), dtype=tt.float64, device=self.device)
+        ascent = tt.empty_like(offset)
+        rmse = tt.empty_like(offset) if want_rmse else None
+        _lib.check(self.lib.imgcorr_linear_fit(self._h, ctypes.c_void_p(frames.data_ptr()), _dtype_code(frames.dtype), n, px, xs,
+                                               float(max_intensity), float(min_ascent), ctypes.c_void_p(offset.data_ptr()),
+                                               ctypes.c_void_p(ascent.data_ptr()), ctypes.c_void_p(rmse.data_ptr()) if want_rmse else None,
+                                               self._stream()))
+        return (offset, ascent, rmse) if want_rmse else (offset, ascent)
+
     def undistort_maps(self):
         tt = torch()
         mapx = tt.empty((self.H, self.W), dtype=tt.float32, device=self.device)

@@ -198,6 +198,26 @@ IMGCORR_API int imgcorr_ste_average(imgcorr_ctx* ctx, const void* frames_dev, in
 IMGCORR_API int imgcorr_ste_average_thr(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, double* avg_dev,
                             uint8_t* mask_dev, const double* threshold_dev, void* stream);
 
+/* ---- K5: calibration-map producers ---------------------------------------------------
+ * Float64 streaming reductions over small stacks of frames; frame sizes are free (the context only supplies the device).
+ *
+ * imgcorr_stack_mean: imgAverage (transform/imgAverage.py:7-22) of n frames of `elems` samples each (H*W, or H*W*3 for colour
+ *   frames), then optionally  img -= bg  (minus_dev: float64 [elems], or minus_scalar when use_scalar != 0) and, with gray3 != 0,
+ *   toGray (transformations.py:126-135) over the 3 interleaved channels -> out_dev float64 [elems] or [elems / 3].  Together
+ *   with imgcorr_subsample_f64 (img[::10, ::10]), the 3x3 median (imgcorr_pointwise_median) and imgcorr_scale_f64 (img /= mx)
+ *   this is flatFieldFromCloseDistance (camera/flatField/flatFieldFromCloseDistance.py:16-38).
+ * imgcorr_linear_fit: getLinearityFunction (camera/DarkCurrentMap.py:61-80): per-pixel line  image(t) = offset + ascent t
+ *   through n frames taken at exposure times x[n], samples above max_intensity masked, NaN ascents set to 0 and ascents below
+ *   min_ascent folded into the offset.  rmse_dev may be NULL.  The regression restates fancytools'
+ *   linRegressUsingMasked2dArrays (absent from the reference tree: parity unpinned for that ingredient, see oracle/producers.py). */
+IMGCORR_API int imgcorr_stack_mean(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, size_t elems, const double* minus_dev,
+                       double minus_scalar, int use_scalar, int gray3, double* out_dev, void* stream);
+IMGCORR_API int imgcorr_scale_f64(imgcorr_ctx* ctx, double* data_dev, size_t elems, double divisor, void* stream);
+IMGCORR_API int imgcorr_subsample_f64(imgcorr_ctx* ctx, const double* src_dev, int height, int width, int step_y, int step_x, double* dst_dev,
+                          void* stream);
+IMGCORR_API int imgcorr_linear_fit(imgcorr_ctx* ctx, const void* frames_dev, int dtype, int n_frames, size_t pixels, const double* x_host,
+                       double max_intensity, double min_ascent, double* offset_dev, double* ascent_dev, double* rmse_dev, void* stream);
+
 /* ---- self-test ---------------------------------------------------------------------------------------
  * K1 and K4 divide in float64 with a shortened Newton sequence (MUFU.RCP64H seed, one refinement, residual correction:
  * csrc/imgcorr_core.cuh rcp_f32range / ddiv_rcp) that is exact only because the divisors are float32-derived or small

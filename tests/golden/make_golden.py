@@ -332,8 +332,71 @@ def ste_nlf():
     save('ste_nlf', frames=frames, dark=dark, flat=flat, K=synth.camera_matrix(params_l), dist=synth.dist_coeffs(params_l), **out)
 
 
+def producers():
+    """flatFieldFromCloseDistance, averageSameExpTimes / getDarkCurrentAverages and the map-derived lens
+    utilities of the unmodified reference (getLinearityFunction needs the absent fancytools regression: unpinned)."""
+    ref_shim.install_masked_moving_average()
+    import importlib
+    import types
+    import imgProcessor.features.SingleTimeEffectDetection as stemod
+    importlib.reload(stemod)
+    for name in ('imgProcessor.utils.baseClasses',):
+        if name not in sys.modules:
+            try:
+                importlib.import_module(name)
+            except Exception:
+                m = types.ModuleType(name)
+                m.Iteratives = type('Iteratives', (object,), {'__init__': lambda self, **k: None})
+                sys.modules[name] = m
+    import imgProcessor.camera.DarkCurrentMap as dcm
+    importlib.reload(dcm)
+    from imgProcessor.camera.flatField.flatFieldFromCloseDistance import flatFieldFromCloseDistance
+    rng = np.random.default_rng(5)
+    H, W = 90, 130
+    out = {}
+    flat = synth.flat_map(H, W, p_zero=0).astype(np.float64)
+    imgs = [np.clip(np.rint(flat[..., None] * np.array([900.0, 1400.0, 700.0]) + 40 + rng.normal(0, 6, (H, W, 3))), 0, 65535).astype(np.uint16)
+            for _ in range(4)]
+    bgs = [np.clip(np.rint(40 + rng.normal(0, 3, (H, W, 3))), 0, 65535).astype(np.uint16) for _ in range(3)]
+    out['ff_imgs'], out['ff_bgs'] = np.stack(imgs), np.stack(bgs)
+    out['ff_bglist'] = flatFieldFromCloseDistance(list(imgs), list(bgs))
+    out['ff_bgnum'] = flatFieldFromCloseDistance(list(imgs), 41.5)
+    out['ff_f32'] = flatFieldFromCloseDistance([i.astype(np.float32) for i in imgs], [b.astype(np.float32) for b in bgs])
+    # dark-current averages per exposure time (DarkCurrentMap: STE removal with nStd=3, NLF estimated from the images)
+    Hd, Wd = 120, 160
+    dark = synth.dark_map(Hd, Wd).astype(np.float64)
+    times = [1.0, 1.0, 1.0, 4.0, 4.0, 4.0, 4.0, 9.0]
+    frames = []
+    for t in times:
+        f = dark + 2.5 * t + rng.normal(0, 2.0 + 0.2 * t, (Hd, Wd))
+        y, x = rng.integers(2, Hd - 4), rng.integers(2, Wd - 4)
+        f[y:y + 2, x:x + 3] += 700.0
+        frames.append(np.clip(np.rint(f), 0, 65535).astype(np.uint16))
+    out['dc_times'], out['dc_frames'] = np.array(times), np.stack(frames)
+    out['dc_avg_t4'] = dcm.averageSameExpTimes(list(frames[3:7]))
+    xs, av = dcm.getDarkCurrentAverages(times, frames)
+    out['dc_x'], out['dc_averages'] = np.array(xs), av
+    # map-derived lens utilities (LensDistortion.py:332-340, 382-402)
+    Hl, Wl = 96, 128
+    lens = make_lens(synth.lens_moderate(Hl, Wl), (Hl, Wl))
+    mx, my = lens.getDistortRectifyMap(Wl, Hl)
+    out['lens_K'], out['lens_dist'] = lens.coeffs['cameraMatrix'], lens.coeffs['distortionCoeffs']
+    out['lens_dmapx'], out['lens_dmapy'] = mx, my
+    out['lens_shift'] = lens.getShift(Wl, Hl)
+    ux, uy = lens.getDeflection(Wl, Hl)
+    out['lens_ux'], out['lens_uy'] = ux, uy
+    img8 = synth.scene(Hl, Wl, 4, np.uint8)
+    imgf = synth.scene(Hl, Wl, 5, np.float32)
+    out['lens_img8'], out['lens_imgf'] = img8, imgf
+    out['lens_distort8'] = lens.distortImage(img8)
+    out['lens_distortf'] = lens.distortImage(imgf)
+    save('producers', **out)
+
+
 if __name__ == '__main__':
-    if sys.argv[1:] == ['ste_nlf']:
+    if sys.argv[1:] == ['producers']:
+        producers()
+    elif sys.argv[1:] == ['ste_nlf']:
         ste_nlf()
     elif sys.argv[1:] == ['perspective']:
         perspective()
@@ -344,3 +407,4 @@ if __name__ == '__main__':
         perspective()
         ste()
         ste_nlf()
+        producers()
