@@ -6,7 +6,7 @@ imgProcessor.camera.flatField.flatFieldFromCloseDistance.flatFieldFromCloseDista
     bg  = getBackground2(bg_imgs, img)             utils/getBackground2.py:5-12   (average of bg_imgs, or a number)
     img -= bg
     img = toGray(img)                              transformations.py:126-135     (colour frames: luminance weights)
-    mx  = median_filter(img[::10, ::10], 3).max()
+    mx  = max of the 3x3 median filter of img[::10, ::10]
     img /= mx
 
 Kernel K5 (csrc/k5_producers.cu) does the average / background / luminance in one streaming pass and the final scaling,

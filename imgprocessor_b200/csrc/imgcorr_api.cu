@@ -299,6 +299,7 @@ static int upload_map(imgcorr_ctx* c, float** slot, const float* src, int on_dev
         return IMGCORR_OK;
     }
     if (!*slot) CK(cudaMalloc((void**)slot, bytes));
+    else CK(cudaDeviceSynchronize());      // launches on other (non-blocking) streams may still read the map being replaced
     CK(cudaMemcpy(*slot, src, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     std::vector<float> tmp;
     const float* h = src;
@@ -350,6 +351,7 @@ extern "C" IMGCORR_API int imgcorr_set_flat(imgcorr_ctx* c, const float* flat, i
     }
     c->flat_absmin = mn;
     if (!c->flat_nz) CK(cudaMalloc((void**)&c->flat_nz, h.size() * sizeof(float)));
+    else CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(c->flat_nz, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
     return IMGCORR_OK;
 }
@@ -845,6 +847,11 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
     }
     const int ns = (int)c->slots.size();
     const int chunks = (n_frames + G - 1) / G;
+    // whatever happens below, no copy from / into the caller's buffers may still be in flight when this call returns
+    struct Drain {
+        imgcorr_ctx* c; bool armed = true;
+        ~Drain() { if (armed) { cudaStreamSynchronize(c->s_in); cudaStreamSynchronize(c->s_k); cudaStreamSynchronize(c->s_out); } }
+    } drain{c};
     auto frames_of = [&](int k) { return n_frames - k * G < G ? n_frames - k * G : G; };
     auto retire = [&](int k) -> int {          // chunk k's D2H has been enqueued on s_out in slot k % ns
         HostSlot& s = c->slots[k % ns];
@@ -871,6 +878,7 @@ extern "C" IMGCORR_API int imgcorr_correct_host(imgcorr_ctx* c, const void* raw_
         CK(cudaEventRecord(s.ev_out, c->s_out));
     }
     for (int k = (chunks > ns ? chunks - ns : 0); k < chunks; ++k) { r = retire(k); if (r) return r; }
+    drain.armed = false;                               // every chunk was retired: nothing is in flight
     return IMGCORR_OK;
 }
 

@@ -93,6 +93,17 @@ class Engine(object):
         _lib.check(self.lib.imgcorr_selftest_division(self._h, int(numerators_per_divisor), int(seed), buf))
         return int(buf[0]), float(buf[1])
 
+    def _check_out(self, out, shape, what='out'):
+        """a caller-supplied output tensor goes to the kernels by pointer: refuse anything that is not exactly what they write"""
+        tt = torch()
+        if not isinstance(out, tt.Tensor) or not out.is_cuda or out.device != self.device:
+            raise ValueError('%s must be a CUDA tensor on %s' % (what, self.device))
+        if tuple(out.shape) != tuple(shape):
+            raise ValueError('%s has shape %s, expected %s' % (what, tuple(out.shape), tuple(shape)))
+        if not out.is_contiguous():
+            raise ValueError('%s must be contiguous' % what)
+        return out
+
     def _stream(self):
         return ctypes.c_void_p(torch().cuda.current_stream(self.device).cuda_stream)
 
@@ -203,6 +214,8 @@ class Engine(object):
         out = kw.get('out')
         if out is None:
             out = tt.empty((n_frames, oh, ow), dtype=kw.get('out_dtype') or tt.float32, device=self.device)
+        else:
+            self._check_out(out, (n_frames, oh, ow))
         with self.ingest(big_endian, gap):
             _lib.check(self.lib.imgcorr_correct_batch(
                 self._h, ctypes.c_void_p(buf.data_ptr() + offset), _dtype_code(dtype), ctypes.c_void_p(out.data_ptr()),
@@ -224,6 +237,8 @@ class Engine(object):
             out_dtype = tt.float64 if raw.dtype == tt.float64 else tt.float32
         if out is None:
             out = tt.empty((n, self.H, self.W), dtype=out_dtype, device=self.device)
+        else:
+            self._check_out(out, (n, self.H, self.W))
         mask = tt.zeros((n, self.H, self.W), dtype=tt.uint8, device=self.device) if want_mask else None
         _lib.check(self.lib.imgcorr_pointwise_median(
             self._h, ctypes.c_void_p(raw.data_ptr()), rc, ctypes.c_void_p(out.data_ptr()), _dtype_code(out.dtype),
@@ -245,6 +260,8 @@ class Engine(object):
             out_dtype = src.dtype
         if out is None:
             out = tt.empty((n, oh, ow), dtype=out_dtype, device=self.device)
+        else:
+            self._check_out(out, (n, oh, ow))
         _lib.check(self.lib.imgcorr_undistort(
             self._h, ctypes.c_void_p(src.data_ptr()), _dtype_code(src.dtype), ctypes.c_void_p(out.data_ptr()),
             _dtype_code(out.dtype), n, float(border_value), x0, y0, ow, oh, self._stream()))
@@ -410,6 +427,8 @@ class Engine(object):
         x0, y0, ow, oh = self._window(window if lens else None)
         if out is None:
             out = tt.empty((n, oh, ow), dtype=out_dtype or tt.float32, device=self.device)
+        else:
+            self._check_out(out, (oh, ow) if squeeze and out.dim() == 2 else (n, oh, ow))
         _lib.check(self.lib.imgcorr_correct_batch(
             self._h, ctypes.c_void_p(raw.data_ptr()), _dtype_code(raw.dtype), ctypes.c_void_p(out.data_ptr()),
             _dtype_code(out.dtype), n, float(threshold), int(ksize), int(flags), int(lens), float(border_value),
@@ -509,14 +528,21 @@ def to_numpy(t, threads=8):
     return out
 
 
-_ENGINES = {}
+_ENGINES = {}          # (device, H, W) -> Engine, least recently used first
+MAX_CACHED_ENGINES = 16
 
 
 def get_engine(height, width, device=None):
+    """the cached engine (context: calibration copies, scratch, pinned rings) for a device and frame shape.  At most
+    MAX_CACHED_ENGINES are kept; the least recently used one is closed (its device memory freed) when a new shape arrives."""
     tt = require_cuda()
     idx = tt.cuda.current_device() if device is None else tt.device('cuda', device).index
     key = (idx, int(height), int(width))
-    e = _ENGINES.get(key)
+    e = _ENGINES.pop(key, None)
     if e is None or e._h is None:
-        e = _ENGINES[key] = Engine(height, width, idx)
+        e = Engine(height, width, idx)
+        while len(_ENGINES) >= MAX_CACHED_ENGINES:
+            old = _ENGINES.pop(next(iter(_ENGINES)))
+            old.close()
+    _ENGINES[key] = e
     return e
