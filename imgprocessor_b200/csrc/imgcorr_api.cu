@@ -432,6 +432,7 @@ extern "C" IMGCORR_API int imgcorr_pointwise_median(imgcorr_ctx* c, const void* 
     K1Args a;
     int r = fill_k1(c, a, raw_dev, raw_dtype, out_dev, mask_dev, n_frames, threshold, ksize, cond, flags);
     if (r) return r;
+    a.out_streaming = 1;
     int l = 0;
     cudaError_t e = launch_k1(a, raw_dtype, out_dtype, c->k1_variant, c->sm_count, c->k1_seg_rows, (cudaStream_t)stream, &l);
     c->launches += l;

@@ -28,6 +28,7 @@ struct K1Args {
     int maps_finite;        // dark / flat hold no NaN / inf (checked once at upload)
     const float* flat_nz;   // copy of flat with zeros replaced by 1.0 (unconditional division), or null
     void* dump;             // >= 2 * grid * threads * 8 bytes of scratch: lanes without an output pixel store here
+    int out_streaming;      // the output is not consumed by a following kernel of the same call (K1-only entry point): L2 evict-first
     int no_overflow;        // the calibration proves |raw - dark| / |flat| < FLT_MAX for this raw dtype: nan_to_num is the identity
     PointwiseConst pw;
     PredicateConst pred;

@@ -33,9 +33,9 @@ constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
 // wins, so both are built.  Batches of float32-output frames run two frames per unit (KsPair).
 template <int R_, int NSTAGE_, int MINB_, int NF_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_, NF = NF_; };
 #ifndef KS_NARROW_R
-#define KS_NARROW_R 8
-#define KS_NARROW_NSTAGE 4
-#define KS_NARROW_MINB 5
+#define KS_NARROW_R 16
+#define KS_NARROW_NSTAGE 3
+#define KS_NARROW_MINB 3
 #endif
 typedef KsShape<KS_NARROW_R, KS_NARROW_NSTAGE, KS_NARROW_MINB, 1> KsNarrow;
 #ifndef KS_WIDE_R
@@ -44,10 +44,16 @@ typedef KsShape<KS_NARROW_R, KS_NARROW_NSTAGE, KS_NARROW_MINB, 1> KsNarrow;
 #define KS_WIDE_MINB 3
 #endif
 typedef KsShape<KS_WIDE_R, KS_WIDE_NSTAGE, KS_WIDE_MINB, 1> KsWide;
+#ifndef KS_L2_HINTS
+#define KS_L2_HINTS 1
+#endif
+#ifndef KS_FIRST_FAST
+#define KS_FIRST_FAST 1
+#endif
 #ifndef KS_PAIR_R
 #define KS_PAIR_R 16
 #define KS_PAIR_NSTAGE 3
-#define KS_PAIR_MINB 2
+#define KS_PAIR_MINB 3
 #endif
 typedef KsShape<KS_PAIR_R, KS_PAIR_NSTAGE, KS_PAIR_MINB, 2> KsPair;
 constexpr int KS_MAPW = 128;                // float32 box: tx0-4 .. tx0+123
@@ -75,6 +81,12 @@ template <typename OutT> __device__ __forceinline__ OutT ks_out(float v);
 template <> __device__ __forceinline__ float    ks_out<float>(float v)    { return v; }
 template <> __device__ __forceinline__ uint16_t ks_out<uint16_t>(float v) { return sat_u16(v); }
 template <> __device__ __forceinline__ uint8_t  ks_out<uint8_t>(float v)  { return sat_u8(v); }
+
+// store with an L2 eviction-priority hint (float32 results of the straight-line chunks)
+template <typename OutT> __device__ __forceinline__ void ks_store(OutT* p, OutT v, uint64_t) { *p = v; }
+template <> __device__ __forceinline__ void ks_store<float>(float* p, float v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(policy) : "memory");
+}
 
 __device__ __noinline__ bool ks_exact(float x, float b, double thr, int cond) {
     PredicateConst pc;
@@ -180,11 +192,17 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                 uint8_t* base = smem + (size_t)stage * B::stage_bytes;
                 const int y = u.yl0 + k * KS_R;
                 mbar_expect_tx(&full[stage], tx_bytes);
+                // L2 priorities: raw samples stream through once (evict first), the calibration maps are read again by every
+                // frame of this launch and by the next launch (evict last): a one-frame launch then finds most of its 8 B/px of
+                // dark / flat in L2 instead of DRAM
 #pragma unroll
                 for (int f = 0; f < NF; ++f)
-                    tma_load_3d(base + f * B::raw_bytes, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame + f);
-                if (has_dark) tma_load_2d(base + NF * B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y);
-                if (has_flat) tma_load_2d(base + NF * B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y);
+                    tma_load_3d_hint(base + f * B::raw_bytes, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame + f,
+                                     KS_L2_HINTS ? L2_EVICT_FIRST : L2_EVICT_NORMAL);
+                if (has_dark) tma_load_2d_hint(base + NF * B::raw_bytes, &tm_dark, &full[stage], u.tx0 - KS_MAPX, y,
+                                               KS_L2_HINTS ? L2_EVICT_LAST : L2_EVICT_NORMAL);
+                if (has_flat) tma_load_2d_hint(base + NF * B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - KS_MAPX, y,
+                                               KS_L2_HINTS ? L2_EVICT_LAST : L2_EVICT_NORMAL);
             }
         }
         return;
@@ -197,6 +215,9 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
     pred.lo = sconst[0]; pred.hi = sconst[1]; pred.thr = *(const double*)(sconst + 2);
     if (CFG >= 0) pred.cond = (CFG & KS_LT) ? COND_LT : COND_GT;
     const int lc = warp * KS_SW - 1 + lane;            // strip-local column of this lane: -1 .. 120
+    // results that nobody reads back soon (a K1-only call) leave L2 first, so that the calibration maps stay; inside the
+    // chain K2 reads them right away and they keep the normal priority
+    const uint64_t out_policy = (KS_L2_HINTS && a.out_streaming) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
     const ptrdiff_t frame_px = (ptrdiff_t)H * W;
     uint32_t g = 0;
 
@@ -305,10 +326,12 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                 }
             }
             const int rows = u.n_in - k * KS_R;
-            if (k > 0 && rows >= KS_R) {
-                // steady state: every row emits; the store is unconditional (lanes without an output pixel write to
+            if ((KS_FIRST_FAST || k > 0) && rows >= KS_R) {
+                // straight-line chunk: every row emits; the store is unconditional (lanes without an output pixel write to
                 // a private scratch slot) and the guard-band test is only accumulated — if any lane of the warp hit the
-                // band in this chunk (rare), the chunk is redone below with the exact predicate.
+                // band in this chunk (rare), the chunk is redone below with the exact predicate.  A unit's FIRST chunk goes
+                // through here as well: its first one or two steps belong to rows above the unit (the halo row, and the
+                // priming step of the vertical 'reflect'), so only their stores are redirected to the scratch slot.
                 Sorted3<float> k0[NF], k1[NF];
                 float kc[NF];
                 OutT* op[NF];
@@ -318,8 +341,10 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                     op[f] = valid ? outp + f * frame_px
                                   : (OutT*)a.dump + ((size_t)f * gridDim.x + blockIdx.x) * KS_THREADS + threadIdx.x;
                 }
-                uint8_t* mp = has_mask ? (valid ? maskp : (uint8_t*)a.dump + (size_t)(gridDim.x + blockIdx.x) * KS_THREADS * sizeof(OutT) + threadIdx.x) : nullptr;
+                uint8_t* const mdump = (uint8_t*)a.dump + (size_t)(gridDim.x + blockIdx.x) * KS_THREADS * sizeof(OutT) + threadIdx.x;
+                uint8_t* mp = has_mask ? (valid ? maskp : mdump) : nullptr;
                 const int ostride = valid ? W : 0;       // element index j * ostride stays below 2^31 (R * 32767)
+                const bool skip0 = k == 0, skip1 = k == 0 && i_first == 2;      // steps of this chunk that emit nothing
                 bool unsure = false;
 #pragma unroll
                 for (int j = 0; j < KS_R; j += 2) {
@@ -330,9 +355,16 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                     for (int f = 0; f < NF; ++f) {
                         const float xa = pixel(base, j, f, ma);
                         const float xb = pixel(base, j + 1, f, mb);
+                        OutT* d0 = op[f] + j * ostride;
+                        OutT* d1 = op[f] + (j + 1) * ostride;
+                        if (j == 0) {
+                            OutT* const dumpp = (OutT*)a.dump + ((size_t)f * gridDim.x + blockIdx.x) * KS_THREADS + threadIdx.x;
+                            d0 = skip0 ? dumpp : d0;
+                            d1 = skip1 ? dumpp : d1;
+                        }
                         if (nomed) {
-                            op[f][j * ostride] = ks_out<OutT>(c1[f]);
-                            op[f][(j + 1) * ostride] = ks_out<OutT>(xa);
+                            ks_store<OutT>(d0, ks_out<OutT>(c1[f]), out_policy);
+                            ks_store<OutT>(d1, ks_out<OutT>(xa), out_policy);
                             c1[f] = xb;
                             continue;
                         }
@@ -342,9 +374,12 @@ k1_stream_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_consta
                         bool r1, r2;
                         unsure |= !predicate_certain(c1[f], m1, pred, r1);
                         unsure |= !predicate_certain(xa, m2, pred, r2);
-                        op[f][j * ostride] = ks_out<OutT>(r1 ? m1 : c1[f]);
-                        op[f][(j + 1) * ostride] = ks_out<OutT>(r2 ? m2 : xa);
-                        if (has_mask) { mp[j * ostride] = r1 ? 1 : 0; mp[(j + 1) * ostride] = r2 ? 1 : 0; }
+                        ks_store<OutT>(d0, ks_out<OutT>(r1 ? m1 : c1[f]), out_policy);
+                        ks_store<OutT>(d1, ks_out<OutT>(r2 ? m2 : xa), out_policy);
+                        if (has_mask) {
+                            *((j == 0 && skip0) ? mdump : mp + j * ostride) = r1 ? 1 : 0;
+                            *((j == 0 && skip1) ? mdump : mp + (j + 1) * ostride) = r2 ? 1 : 0;
+                        }
                         s0[f] = ta; s1[f] = tb; c1[f] = xb;
                     }
                 }
