@@ -180,10 +180,12 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    golden = golden_check()
     cores = os.cpu_count() or 1
     ctx = mp.get_context('fork')
+    # the workers are forked BEFORE this process touches OpenCV / scipy: forking a process whose OpenCV thread pool already
+    # runs can deadlock the children.  The golden check then runs here, in the parent, before anything is timed.
     with ctx.Pool(cores, initializer=_ref_worker_init) as pool:
+        golden = golden_check()
         for _ in range(max(args.warmup, 1)):
             pool.map(_ref_worker_step, range(cores))
         t0 = time.perf_counter()

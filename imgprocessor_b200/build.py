@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 OBJ = os.path.join(ROOT, 'build', 'imgcorr')
 LIB = os.path.join(PKG, 'libimgcorr.so')
 SOURCES = ['k1_pointwise_median.cu', 'k1_stream.cu', 'k1_stream5.cu', 'k2_undistort.cu', 'k3_warp.cu', 'k4_ste.cu', 'selftest.cu', 'k5_producers.cu', 'imgcorr_api.cu']
-HEADERS = [os.path.join(CSRC, 'imgcorr_core.cuh'), os.path.join(CSRC, 'imgcorr_kernels.cuh'), os.path.join(CSRC, 'imgcorr_tma.cuh'), os.path.join(CSRC, 'imgcorr_warp.cuh'), os.path.join(CSRC, 'imgcorr_ste.cuh'), os.path.join(CSRC, 'median25_net.inc'),
+HEADERS = [os.path.join(CSRC, 'imgcorr_core.cuh'), os.path.join(CSRC, 'imgcorr_kernels.cuh'), os.path.join(CSRC, 'imgcorr_tma.cuh'), os.path.join(CSRC, 'imgcorr_warp.cuh'), os.path.join(CSRC, 'imgcorr_ste.cuh'), os.path.join(CSRC, 'median25_net.inc'), os.path.join(CSRC, 'median25_pair_net.inc'),
            os.path.join(ROOT, 'include', 'imgcorr.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC,-ffp-contract=off,-fvisibility=hidden', '--expt-relaxed-constexpr']

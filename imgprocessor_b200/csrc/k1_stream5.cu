@@ -83,6 +83,9 @@ __device__ __noinline__ bool exact5(float x, float b, double thr, int cond) {
 #ifndef K5_INTKEYS
 #define K5_INTKEYS 1
 #endif
+#ifndef K5_PAIR
+#define K5_PAIR 1
+#endif
 #if K5_INTKEYS
 typedef OrdKey K5T;                         // the window holds order-preserving integer keys (see imgcorr_core.cuh)
 __device__ __forceinline__ K5T k5_in(float x) { return to_key(x); }
@@ -97,6 +100,38 @@ __device__ __forceinline__ K5T k5_shfl_up(K5T c, int d) { return __shfl_up_sync(
 __device__ __forceinline__ K5T k5_shfl_down(K5T c, int d) { return __shfl_down_sync(0xffffffffu, c, d); }
 #endif
 struct Q5 { K5T v[5]; };                    // sorted horizontal quintuple of one row
+
+// Row-pair scheme (median25_pair_net.inc, tools/gen_median25_pair.py): two vertically adjacent windows share four of their
+// five rows.  Net A reduces the four shared sorted quintuples to the six values of rank 7..12 (the only ones of the 20
+// that can be a median of 25), once per PAIR of output rows; net B picks rank 5 of those six plus the window's own fifth
+// row, once per output row.  38 + 14/2 exchanges per pair and 3 + 10/2 per row instead of 57 per row.
+#include "median25_pair_net.inc"
+struct Band6 { K5T v[6]; };
+__device__ __forceinline__ Band6 band_of_four(const Q5& r0, const Q5& r1, const Q5& r2, const Q5& r3) {
+    K5T v[20];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { v[k] = r0.v[k]; v[5 + k] = r1.v[k]; v[10 + k] = r2.v[k]; v[15 + k] = r3.v[k]; }
+#define M25_CE(a, b) cswap(v[a], v[b]);
+#define M25_LO(a, b) v[a] = vmin(v[a], v[b]);
+#define M25_HI(a, b) v[b] = vmax(v[a], v[b]);
+    M25A_NET
+    Band6 b;
+    b.v[0] = v[M25A_BAND0]; b.v[1] = v[M25A_BAND1]; b.v[2] = v[M25A_BAND2];
+    b.v[3] = v[M25A_BAND3]; b.v[4] = v[M25A_BAND4]; b.v[5] = v[M25A_BAND5];
+    return b;
+}
+__device__ __forceinline__ K5T median_band_row(const Band6& b, const Q5& own) {
+    K5T v[11];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v[k] = b.v[k];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[6 + k] = own.v[k];
+    M25B_NET
+#undef M25_CE
+#undef M25_LO
+#undef M25_HI
+    return v[M25B_RESULT];
+}
 
 struct Unit5 {
     int frame, tx0, ys, ye, yl0, n_in, nchunk;
@@ -265,6 +300,31 @@ k1_stream5_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
                 OutT* op = valid ? outp : (OutT*)a.dump + (size_t)blockIdx.x * K5_THREADS + threadIdx.x;
                 uint8_t* mp = has_mask ? (valid ? maskp : (uint8_t*)a.dump + (size_t)(gridDim.x + blockIdx.x) * K5_THREADS * sizeof(OutT) + threadIdx.x) : nullptr;
                 const int ostride = valid ? W : 0;
+#if K5_PAIR
+                static_assert(K5_R % 2 == 0, "rows per stage must be even (outputs are produced in vertical pairs)");
+#pragma unroll
+                for (int j = 0; j < K5_R; j += 2) {
+                    // two new rows -> two outputs: windows (w0 w1 w2 w3 qa) and (w1 w2 w3 qa qb) share w1 w2 w3 qa
+                    const float xa = pixel(base, j), xb = pixel(base, j + 1);
+                    const Q5 qa = quint(xa), qb = quint(xb);
+                    const Band6 band = band_of_four(w1, w2, w3, qa);
+                    const float med_a = k5_out(median_band_row(band, w0));
+                    const float med_b = k5_out(median_band_row(band, qb));
+                    bool rep_a, rep_b;
+                    const bool sure_a = predicate_certain(c2, med_a, pred, rep_a);
+                    const bool sure_b = predicate_certain(c1, med_b, pred, rep_b);
+                    if (__any_sync(0xffffffffu, !(sure_a && sure_b))) {
+                        if (!sure_a) rep_a = exact5(c2, med_a, pred.thr, pred.cond);
+                        if (!sure_b) rep_b = exact5(c1, med_b, pred.thr, pred.cond);
+                    }
+                    op[0] = out5<OutT>(rep_a ? med_a : c2);
+                    op[ostride] = out5<OutT>(rep_b ? med_b : c1);
+                    if (has_mask) { mp[0] = rep_a ? 1 : 0; mp[ostride] = rep_b ? 1 : 0; mp += 2 * ostride; }
+                    op += 2 * ostride;
+                    push(qa, xa);
+                    push(qb, xb);
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < K5_R; ++j) {
                     const float x = pixel(base, j);
@@ -280,6 +340,7 @@ k1_stream5_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
                     op += ostride;
                     push(q, x);
                 }
+#endif
                 outp += (size_t)K5_R * W;
                 if (has_mask) maskp += (size_t)K5_R * W;
                 i += K5_R;
