@@ -53,7 +53,7 @@ struct imgcorr_ctx {
     LensConst lens{};
     double* lens_dev = nullptr;
     float4* k2_wtab = nullptr;                // OpenCV's BilinearTab_f [32][32] (K2 tiles)
-    struct GeomKey { int x0, y0, ow, oh, g; };
+    struct GeomKey { int x0, y0, ow, oh, esz, g; };
     std::vector<GeomKey> k2_geom;             // staged-box geometry per output window (k2_pick_geometry), reset by set_lens
     // K2 coordinate cache: packed per-pixel source coordinates of the current lens for an output window (4 bytes per pixel),
     // written by the first tiled launch, read by the following ones; dropped by set_lens
@@ -474,12 +474,13 @@ static int run_k2(imgcorr_ctx* c, const void* src, int sdt, void* dst, int ddt, 
     a.geometry = 0;
     if (!mapx) {
         bool found = false;
+        const int gesz = (int)dtype_size(sdt) > 4 ? 4 : (int)dtype_size(sdt);
         for (const auto& k : c->k2_geom)
-            if (k.x0 == x0 && k.y0 == y0 && k.ow == ow && k.oh == oh) { a.geometry = k.g; found = true; break; }
+            if (k.x0 == x0 && k.y0 == y0 && k.ow == ow && k.oh == oh && k.esz == gesz) { a.geometry = k.g; found = true; break; }
         if (!found) {
-            a.geometry = k2_pick_geometry(c->lens, c->H, c->W, x0, y0, ow, oh);
+            a.geometry = k2_pick_geometry(c->lens, c->H, c->W, x0, y0, ow, oh, gesz);
             if (c->k2_geom.size() > 64) c->k2_geom.clear();
-            c->k2_geom.push_back({x0, y0, ow, oh, a.geometry});
+            c->k2_geom.push_back({x0, y0, ow, oh, gesz, a.geometry});
         }
     }
     // coordinate cache (tiled variant, analytic map): the first launch for this lens / window writes it, later ones read it

@@ -67,7 +67,7 @@ struct K2Args {
 };
 void k2_cache_size(int geometry, int ow, int oh, size_t* words, size_t* tiles);
 bool k2_will_tile(const K2Args& a, int src_dtype, int dst_dtype, int variant);    // launch_k2 takes the tiled variant
-int k2_pick_geometry(const LensConst& lens, int H, int W, int x0, int y0, int ow, int oh);
+int k2_pick_geometry(const LensConst& lens, int H, int W, int x0, int y0, int ow, int oh, int src_elem_size);
 
 // order of the doubles in K2Args::lens_dev
 enum LensPack : int { LP_K1, LP_K2, LP_K3, LP_P1, LP_P2, LP_P1X2, LP_P2X2, LP_FX, LP_FY, LP_CX, LP_CY, LP_IR0, LP_IR2, LP_IR4, LP_IR5, LP_PAD, LP_COUNT };

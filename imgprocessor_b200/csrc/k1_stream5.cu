@@ -194,9 +194,10 @@ k1_stream5_kernel(const __grid_constant__ CUtensorMap tm_raw, const __grid_const
                 uint8_t* base = smem + (size_t)stage * B::stage_bytes;
                 const int y = u.yl0 + k * K5_R;
                 mbar_expect_tx(&full[stage], tx_bytes);
-                tma_load_3d(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame);
-                if (has_dark) tma_load_2d(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - K5_MAPX, y);
-                if (has_flat) tma_load_2d(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - K5_MAPX, y);
+                // L2 priorities as in k1_stream.cu: raw samples pass once, the calibration maps are read again by every frame / launch
+                tma_load_3d_hint(base, &tm_raw, &full[stage], (u.tx0 / B::GRAN) * B::GRAN - B::XOFF, y, u.frame, L2_EVICT_FIRST);
+                if (has_dark) tma_load_2d_hint(base + B::raw_bytes, &tm_dark, &full[stage], u.tx0 - K5_MAPX, y, L2_EVICT_LAST);
+                if (has_flat) tma_load_2d_hint(base + B::raw_bytes + B::map_bytes, &tm_flat, &full[stage], u.tx0 - K5_MAPX, y, L2_EVICT_LAST);
             }
         }
         return;

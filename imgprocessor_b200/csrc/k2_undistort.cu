@@ -241,9 +241,10 @@ template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeo
 #ifndef KT_MINB_V
 #define KT_MINB_V 4
 #endif
-typedef KtGeom<64, 16, 80, 32, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens
-typedef KtGeom<64, 16, 112, 48, 2, 4> KtG1;                      // strong distortion (window up to ~1.5 x the tile)
-typedef KtGeom<32, 16, 112, 64, 2, 4> KtG2;                      // extreme distortion / large shear
+typedef KtGeom<64, 16, 80, 32, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens (float32 frames)
+typedef KtGeom<64, 16, 96, 32, KT_NBUF_V, KT_MINB_V> KtG1;       // strong lenses (SURVEY's 8192^2 lens needs 84 columns), 16-bit / 8-bit frames
+typedef KtGeom<64, 16, 112, 48, 2, 4> KtG2;                      // very strong distortion (window up to ~1.5 x the tile)
+typedef KtGeom<32, 16, 112, 64, 2, 4> KtG3;                      // extreme distortion / large shear
 constexpr int KT_THREADS = 256;
 constexpr int KT_MARGIN = 3;                                     // pixels added around the estimated window
 // box width per source type: 16-byte origin granularity costs up to 3 / 7 / 15 extra columns (float32 / uint16 / uint8)
@@ -785,10 +786,12 @@ static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
     const bool tstore = a.tma_store && ((size_t)a.ow * sizeof(DstT)) % 16 == 0 && ((uintptr_t)a.dst) % 16 == 0;
     const int g = a.geometry;
     if (tstore) {
+        if (g == 3) return launch_tiled_g<SrcT, DstT, KtG3, true>(a, st);
         if (g == 2) return launch_tiled_g<SrcT, DstT, KtG2, true>(a, st);
         if (g == 1) return launch_tiled_g<SrcT, DstT, KtG1, true>(a, st);
         return launch_tiled_g<SrcT, DstT, KtG0, true>(a, st);
     }
+    if (g == 3) return launch_tiled_g<SrcT, DstT, KtG3, false>(a, st);
     if (g == 2) return launch_tiled_g<SrcT, DstT, KtG2, false>(a, st);
     if (g == 1) return launch_tiled_g<SrcT, DstT, KtG1, false>(a, st);
     return launch_tiled_g<SrcT, DstT, KtG0, false>(a, st);
@@ -796,7 +799,7 @@ static cudaError_t launch_tiled_t(const K2Args& a, cudaStream_t st) {
 
 // words of the coordinate cache for an output window under geometry g (whole tiles) and the number of tiles
 void k2_cache_size(int g, int ow, int oh, size_t* words, size_t* tiles) {
-    const int TW = g == 2 ? KtG2::TW : 64, TH = 16;
+    const int TW = g == 3 ? KtG3::TW : 64, TH = 16;
     const size_t t = (size_t)((ow + TW - 1) / TW) * ((oh + TH - 1) / TH);
     *tiles = t;
     *words = t * (size_t)(TW * TH);
@@ -804,8 +807,9 @@ void k2_cache_size(int g, int ow, int oh, size_t* words, size_t* tiles) {
 
 // Host: the staged-box geometry a lens needs for an output window — the largest source window (plus margins) over all
 // 64x16 tiles, from the exact map at the very 3 x 3 sample points the kernel estimates from.
-// 0: 80x32 box, 1: 112x48, 2: 32-wide tiles with a 112x64 box.  Cached per window by the caller (imgcorr_api.cu).
-int k2_pick_geometry(const LensConst& L, int H, int W, int x0, int y0, int ow, int oh) {
+// 0: 80x32 box, 1: 96x32, 2: 112x48, 3: 32-wide tiles with a 112x64 box.  `src_elem_size` sets the column granularity of the
+// box origin (16 bytes: 4 / 8 / 16 columns).  Cached per window by the caller (imgcorr_api.cu).
+int k2_pick_geometry(const LensConst& L, int H, int W, int x0, int y0, int ow, int oh, int src_elem_size) {
     int need_w = 0, need_h = 0;
     const int TW = 64, TH = 16;
     for (int ty = 0; ty < oh; ty += TH)
@@ -823,13 +827,15 @@ int k2_pick_geometry(const LensConst& L, int H, int W, int x0, int y0, int ow, i
                 ex0 = qx < ex0 ? qx : ex0; ex1 = qx > ex1 ? qx : ex1; ey0 = qy < ey0 ? qy : ey0; ey1 = qy > ey1 ? qy : ey1;
             }
             if (ex1 < 0) continue;
-            const int w = ex1 - ex0 + 2 + 2 * KT_MARGIN + 3, h = ey1 - ey0 + 2 + 2 * KT_MARGIN;   // + 3: 16-byte origin (float32)
+            const int w = ex1 - ex0 + 2 + 2 * KT_MARGIN + (16 / src_elem_size - 1), h = ey1 - ey0 + 2 + 2 * KT_MARGIN;   // + 16-byte origin
             if (w > need_w) need_w = w;
             if (h > need_h) need_h = h;
         }
-    if (need_w <= KtG0::BW && need_h <= KtG0::BH) return 0;
-    if (need_w <= KtG1::BW && need_h <= KtG1::BH) return 1;
-    return 2;
+    const int extra = src_elem_size == 1 ? 16 : 0;          // KtBox widens 8-bit boxes by 16 columns
+    if (need_w <= KtG0::BW + extra && need_h <= KtG0::BH) return 0;
+    if (need_w <= KtG1::BW + extra && need_h <= KtG1::BH) return 1;
+    if (need_w <= KtG2::BW + extra && need_h <= KtG2::BH) return 2;
+    return 3;
 }
 
 __global__ void __launch_bounds__(256) k2_write_maps_kernel(LensConst lens, float* mapx, float* mapy, int H, int W) {
