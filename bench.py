@@ -374,6 +374,8 @@ def run_ours(args):
     cvmaps = lens_setup(eng, H, W, synth.lens_moderate(H, W))
     eng.set_option(_lib.OPT_CHAIN_GROUP, args.group)
     eng.set_option(_lib.OPT_CHAIN_OVERLAP, int(args.overlap))
+    if args.host_slots:
+        eng.set_option(_lib.OPT_HOST_SLOTS, args.host_slots)
 
     numa = {'bound': False} if os.environ.get('IMGCORR_NO_NUMA_BIND') else sharding.bind_host_to_gpu(local)
     raw = synth.scene_torch(F, H, W, 1000 + rank, dev, 'uint16')
@@ -649,6 +651,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-pool', type=int, default=32, help='pinned host frames cycled by the end-to-end leg')
     ap.add_argument('--e2e-steps', type=int, default=3)
+    ap.add_argument('--host-slots', type=int, default=0, help='depth of the pinned / device staging ring of the host-buffer pipeline (0 = library default)')
     ap.add_argument('--strong-total', type=int, default=256, help='frames in total for the strong-scaling point')
     ap.add_argument('--c4-frames', type=int, default=256, help='6000x4000 frames streamed per GPU in the timed region of c4')
     ap.add_argument('--no-configs', action='store_true', help='headline only (skip c0 / c1 / c3 / c4)')

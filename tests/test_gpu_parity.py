@@ -920,6 +920,47 @@ def test_config4_f32_5x5_strong_lens(ip):
     assert np.abs(out - ref).max() / 4095.0 < 1e-3
 
 
+def test_config4_8192_full_size(ip):
+    """configs[3] at its FULL size: one 8192x8192 float32 frame through dark + flat + 5x5 medianThreshold + the strong lens.
+    (1) every 5-bit fixed-point coordinate of the analytic map equals OpenCV's (67 M pixels, compared in slabs);
+    (2) bands of the chain's output (top edge, two interior, bottom edge) equal the band-wise oracle chain evaluated with
+    cv2's own maps, bit for bit — the oracle never holds more than a band, so the test stays within a few GB of host memory."""
+    import cv2
+    from oracle import bands
+    H = W = 8192
+    raw = synth.scene(H, W, 2, np.float32)
+    dark, flat = synth.dark_map(H, W), synth.flat_map(H, W)
+    p = synth.lens_strong(H, W)
+    K, d = synth.camera_matrix(p), synth.dist_coeffs(p)
+    P, roi = cv2.getOptimalNewCameraMatrix(K, d, (W, H), 1, (W, H))
+    mapx, mapy = cv2.initUndistortRectifyMap(K, d, None, P, (W, H), cv2.CV_32FC1)
+    e = ip.engine_mod.Engine(H, W, 0)
+    try:
+        e.set_dark(dark)
+        e.set_flat(flat)
+        e.set_lens(K, d, P)
+        mx, my = e.undistort_maps()
+        mx, my = mx.cpu().numpy(), my.cpu().numpy()
+        for r0 in range(0, H, 1024):
+            a = models.fixed_point_coords(mx[r0:r0 + 1024], my[r0:r0 + 1024])
+            b = models.fixed_point_coords(mapx[r0:r0 + 1024], mapy[r0:r0 + 1024])
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v), r0
+        del mx, my
+        out = e.correct_batch(_dev(raw), 0.1, 5)
+        again = e.correct_batch(_dev(raw), 0.1, 5)                  # second call: K2 reads its coordinate cache
+        assert torch.equal(out, again)
+        for r0, r1 in bands.default_bands(H, 32) + [(1500, 1532), (6000, 6032)]:
+            want = bands.chain_band(raw, dark, flat, mapx, mapy, r0, r1, 0.1, 5)
+            assert np.array_equal(out[r0:r1].cpu().numpy(), want), (r0, r1)
+        k1, mask = e.pointwise_median(_dev(raw), 0.1, 5, flags=0, want_mask=True)          # direct medianThreshold(size=5)
+        for r0, r1 in ((0, 40), (4000, 4040), (H - 40, H)):
+            want = bands.k1_band(raw, None, None, r0, r1, 0.1, 5)
+            assert np.array_equal(k1[r0:r1].cpu().numpy(), want), (r0, r1)
+    finally:
+        e.close()
+
+
 def test_config5_6000x4000_streamed_from_pinned_pool(ip):
     """configs[4]: 6000x4000 uint16 frames cycled from a small pool of pinned buffers through the host-buffer chain; the
     streamed result equals the device-resident chain, and K1 of that chain equals the oracle on a band of rows"""
