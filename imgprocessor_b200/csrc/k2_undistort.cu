@@ -218,20 +218,20 @@ __global__ void __launch_bounds__(K2_BX * K2_BY, K2_MINB) k2_remap_kernel(K2Args
 
 // ------------------------------------------------------------------------------------------------------------
 // Tiled variant (float32 sources — the chain; uint16 / uint8 batches): the source window of a 64x16 output tile is
-// staged in shared memory by ONE TMA box per frame, the four neighbours are gathered from there, and the finished
-// output tile leaves through shared memory as ONE TMA store per frame (cp.async.bulk.tensor, bounds-clipped by the
-// hardware at the frame / roi edge).  The L1 path above spends ~8 L1 wavefronts per 32 pixels on the gather (unaligned,
-// two rows) and is bound by them; shared memory serves the same gather in ~4-5 conflict-free wavefronts, TMA moves whole
-// lines, and the frames of a launch are ring-buffered so the box of frame f+1 lands while frame f is blended.
-//   * the box position is ESTIMATED first by one warp from eight perimeter pixels of the tile (exact coordinates, a
-//     3-pixel margin) and the boxes of the first frames are issued at once, so the DRAM latency of the first box
-//     overlaps the coordinate phase of the whole tile (a single frame per launch used to serialise coordinates ->
-//     TMA wait -> blend per CTA: 61 us per 4096x3000 frame, latency bound);
-//   * coordinates / weights / shared offsets of the tile's pixels are then computed once (4 pixels per thread) and the
-//     exact bounding box of the tile's source window (REDUX + shared atomics) is checked against the estimated box; a
-//     tile whose window is not inside it (never seen with the margin; any map is legal) or does not fit a box at all
-//     (stronger distortion than the launch geometry was chosen for) falls back to global gathers: correct for any map;
-//   * rim pixels (window touching the frame border) are redone from global memory with per-neighbour border handling.
+// staged in shared memory by ONE TMA box per frame and the four neighbours are gathered from there.  The L1 path above
+// spends ~8 L1 wavefronts per 32 pixels on the gather (unaligned, two rows) and is bound by them; shared memory serves the
+// same gather in ~4-5 conflict-free wavefronts, TMA moves whole lines, and the frames of a launch are ring-buffered so the
+// box of frame f+1 lands while frame f is blended.
+//   * the box position is ESTIMATED by warp 0 from nine sample pixels of the tile (3 x 3; exact coordinates, a 3-pixel
+//     margin, clamped to the frame) and the boxes of the first frames are issued at once: their DRAM latency overlaps the
+//     coordinate phase of the other warps;
+//   * coordinates / weights / shared offsets of the tile's pixels are then computed once (4 pixels per thread) and every
+//     pixel is classified against that box: inside -> gathered from shared memory; window entirely outside the frame ->
+//     the border value (written once per frame, no reads); anything else (frame rim, or outside the box: a fraction of a
+//     percent) -> "slow": gathered from global memory with per-neighbour border handling.  A tile whose window does not fit
+//     a box at all (stronger distortion than the launch geometry was chosen for) is all "slow": correct for any map;
+//   * results leave by predicated per-pixel stores (full 128-byte lines per warp) or, optionally, through a shared output
+//     tile and one TMA store per frame (cp.async.bulk.tensor, bounds-clipped by the hardware; measured slower).
 template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeom {
     static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, NBUF = NBUF_, MINB = MINB_;
 };
@@ -240,6 +240,9 @@ template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeo
 #endif
 #ifndef KT_MINB_V
 #define KT_MINB_V 4
+#endif
+#ifndef KT_FPB
+#define KT_FPB 1
 #endif
 typedef KtGeom<64, 16, 80, 32, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens (float32 frames)
 typedef KtGeom<64, 16, 96, 32, KT_NBUF_V, KT_MINB_V> KtG1;       // strong lenses (SURVEY's 8192^2 lens needs 84 columns), 16-bit / 8-bit frames
@@ -516,34 +519,45 @@ k2_tiled_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constan
     }
     DstT* dst = (DstT*)a.dst + (oy0 * ow + ox);
     const int dstep = KT_RSTEP * ow;
+    // KT_FPB frames per CTA barrier: the ring holds KT_NBUF boxes, KT_FPB of them are blended between two barriers and
+    // refilled together (one barrier per frame cost 0.85-2.9 stall cycles per issued instruction in the profiles)
+    constexpr int FPB = (KT_NBUF % KT_FPB == 0 && KT_NBUF >= 2 * KT_FPB) ? KT_FPB : 1;
 #pragma unroll 1
-    for (int f = 0; f < nf; ++f) {
-        if (have_box) {
-            mbar_wait(&full[f % KT_NBUF], (f / KT_NBUF) & 1);
-            const SrcT* box = (const SrcT*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
+    for (int f0 = 0; f0 < nf; f0 += FPB) {
 #pragma unroll
-            for (int j = 0; j < KT_PX; ++j) {
-                const SrcT* p = box + so[j];
-                const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
-                st_if(dst + j * dstep, r, fast & (1u << j));            // predicated store, no branch around the gather
+        for (int g = 0; g < FPB; ++g) {
+            const int f = f0 + g;
+            if (f < nf) {
+                if (have_box) {
+                    mbar_wait(&full[f % KT_NBUF], (f / KT_NBUF) & 1);
+                    const SrcT* box = (const SrcT*)(smem + (f % KT_NBUF) * KT_BOX_BYTES);
+#pragma unroll
+                    for (int j = 0; j < KT_PX; ++j) {
+                        const SrcT* p = box + so[j];
+                        const DstT r = Blend<SrcT, DstT>::run(p[0], p[1], p[BW], p[BW + 1], wt[j]);
+                        st_if(dst + j * dstep, r, fast & (1u << j));            // predicated store, no branch around the gather
+                    }
+                }
+                if (outm) {
+#pragma unroll
+                    for (int j = 0; j < KT_PX; ++j)
+                        if (outm & (1u << j)) dst[j * dstep] = bout;
+                }
+                if (slow) {
+#pragma unroll 1
+                    for (int j = 0; j < KT_PX; ++j)
+                        if (slow & (1u << j)) dst[j * dstep] = slow_pixel(src, j);
+                }
+                src += src_stride;
+                dst += dst_stride;
             }
         }
-        if (outm) {
-#pragma unroll
-            for (int j = 0; j < KT_PX; ++j)
-                if (outm & (1u << j)) dst[j * dstep] = bout;
-        }
-        if (slow) {
-#pragma unroll 1
-            for (int j = 0; j < KT_PX; ++j)
-                if (slow & (1u << j)) dst[j * dstep] = slow_pixel(src, j);
-        }
         if (have_box) {
-            __syncthreads();                           // everyone is done with this buffer
-            if (tid == 0 && f + KT_NBUF < nf) issue(f + KT_NBUF, bx, by);
+            __syncthreads();                           // everyone is done with these buffers
+            if (tid == 0)
+                for (int g = 0; g < FPB; ++g)
+                    if (f0 + g + KT_NBUF < nf) issue(f0 + g + KT_NBUF, bx, by);
         }
-        src += src_stride;
-        dst += dst_stride;
     }
 }
 
