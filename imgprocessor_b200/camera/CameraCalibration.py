@@ -54,6 +54,13 @@ def _map_token(kind, arr):
     call (camera/CameraCalibration.py:500-502, 521-526); `id()` is not part of the key (ids are recycled)."""
     if not isinstance(arr, np.ndarray):
         return None
+    if not arr.flags.writeable and arr.base is None:
+        # a read-only array that owns its memory cannot be edited in place: object identity + address + a sampled hash (in case
+        # the id is recycled by a new array) is enough, and the ~1 ms full pass per map and call is saved.  Mark calibration
+        # arrays read-only (arr.setflags(write=False)) to get this path.
+        flat = arr.reshape(-1)
+        step = max(1, flat.size // 4096)
+        return (kind, 'ro', id(arr), arr.ctypes.data, arr.shape, arr.dtype.str, hash(flat[::step].tobytes()))
     a = arr if arr.flags.c_contiguous else np.ascontiguousarray(arr)
     return (kind, arr.shape, arr.dtype.str, _engine.host_fingerprint(a))
 

@@ -110,6 +110,12 @@ def test_calibration_upload_token_sees_in_place_changes():
         assert t2 != t1, pos
         t1 = t2
     assert _map_token('dark', big.copy()) == t1  # a different object with the same content needs no new upload
+    ro = big.copy()
+    ro.setflags(write=False)                     # read-only owner: identity-keyed fast path, stable across calls
+    assert _map_token('dark', ro) == _map_token('dark', ro) and _map_token('dark', ro)[1] == 'ro'
+    view = big[:]                                # a view of a writeable array is NOT safe: full fingerprint
+    view.setflags(write=False)
+    assert _map_token('dark', view)[1] != 'ro'
     assert _map_token('dark', 3.0) is None
     b = a[::2]                                   # non-contiguous views work too
     assert _map_token('dark', b) == _map_token('dark', b)
