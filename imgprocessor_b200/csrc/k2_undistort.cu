@@ -236,7 +236,7 @@ template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeo
     static constexpr int TW = TW_, TH = TH_, BW = BW_, BH = BH_, NBUF = NBUF_, MINB = MINB_;
 };
 #ifndef KT_NBUF_V
-#define KT_NBUF_V 4
+#define KT_NBUF_V 5
 #endif
 #ifndef KT_MINB_V
 #define KT_MINB_V 4
@@ -244,8 +244,13 @@ template <int TW_, int TH_, int BW_, int BH_, int NBUF_, int MINB_> struct KtGeo
 #ifndef KT_FPB
 #define KT_FPB 1
 #endif
-typedef KtGeom<64, 16, 80, 32, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens (float32 frames)
-typedef KtGeom<64, 16, 96, 32, KT_NBUF_V, KT_MINB_V> KtG1;       // strong lenses (SURVEY's 8192^2 lens needs 84 columns), 16-bit / 8-bit frames
+// 28 rows x 5 boxes in flight instead of 32 x 4 (same shared memory): the moderate 4096x3000 lens needs 27 rows, and the kernel
+// waits on box arrival (19.6 vs 20.1 us per frame); lenses that need 29-32 rows take the 96x32 geometry
+#ifndef KT_BH0
+#define KT_BH0 28
+#endif
+typedef KtGeom<64, 16, 80, KT_BH0, KT_NBUF_V, KT_MINB_V> KtG0;       // every tile of a realistic lens (float32 frames)
+typedef KtGeom<64, 16, 96, 32, 4, KT_MINB_V> KtG1;       // strong lenses (SURVEY's 8192^2 lens needs 84 columns), 16-bit / 8-bit frames
 typedef KtGeom<64, 16, 112, 48, 2, 4> KtG2;                      // very strong distortion (window up to ~1.5 x the tile)
 typedef KtGeom<32, 16, 112, 64, 2, 4> KtG3;                      // extreme distortion / large shear
 constexpr int KT_THREADS = 256;
@@ -577,8 +582,11 @@ template <typename T> static CUtensorMapDataType kt_dtype() {
 template <typename G> struct KcGeom { static constexpr int NBUF = G::BW * G::BH * 4 > 16384 ? 2 : 3; };
 constexpr int KC_MAXT = 256;
 
+#ifndef KC_MINB
+#define KC_MINB 3           // 85 registers: 46 vs 51 us for one 4096x3000 frame with 4 CTAs of 64 registers
+#endif
 template <typename SrcT, typename DstT, typename G, bool TSTORE>
-__global__ void __launch_bounds__(KT_THREADS, G::MINB)
+__global__ void __launch_bounds__(KT_THREADS, KC_MINB)
 k2_cached_kernel(const __grid_constant__ CUtensorMap tm_src, const __grid_constant__ CUtensorMap tm_dst, K2Args a, int tiles_x,
                  long long n_items) {
     constexpr int KT_TW = G::TW, KT_TH = G::TH, KT_BH = G::BH, NBUF = KcGeom<G>::NBUF;
