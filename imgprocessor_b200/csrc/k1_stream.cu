@@ -33,9 +33,9 @@ constexpr int KS_TW = KS_CW * KS_SW;        // 120 output columns per strip
 // wins, so both are built.  Batches of float32-output frames run two frames per unit (KsPair).
 template <int R_, int NSTAGE_, int MINB_, int NF_> struct KsShape { static constexpr int R = R_, NSTAGE = NSTAGE_, MINB = MINB_, NF = NF_; };
 #ifndef KS_NARROW_R
-#define KS_NARROW_R 16
+#define KS_NARROW_R 24
 #define KS_NARROW_NSTAGE 3
-#define KS_NARROW_MINB 3
+#define KS_NARROW_MINB 2
 #endif
 typedef KsShape<KS_NARROW_R, KS_NARROW_NSTAGE, KS_NARROW_MINB, 1> KsNarrow;
 #ifndef KS_WIDE_R
@@ -74,6 +74,7 @@ template <typename RawT, typename C> struct StreamBox {
     static constexpr size_t raw_bytes = (size_t)C::R * BOXW * sizeof(RawT);     // multiples of 128
     static constexpr size_t map_bytes = (size_t)C::R * KS_MAPW * sizeof(float);
     static constexpr size_t stage_bytes = C::NF * raw_bytes + 2 * map_bytes;    // raw[NF] | dark | flat
+    static_assert(raw_bytes % 128 == 0 && map_bytes % 128 == 0, "TMA destinations must be 128-byte aligned: rows per stage must be a multiple of 8");
     static constexpr size_t bar_off = C::NSTAGE * stage_bytes;
     static constexpr size_t total = bar_off + 2 * C::NSTAGE * sizeof(uint64_t) + 64;
 };

@@ -579,7 +579,10 @@ template <typename T> static CUtensorMapDataType kt_dtype() {
 // (the analytic kernel above serialises box latency -> blend -> store per CTA and is issue bound on top of that).
 // Per item: wait, (new tile: unpack offsets, weights from OpenCV's table, pixel classes), four shared-memory gathers and
 // the blend per pixel, output tile to shared memory, one TMA store.  No lens arithmetic except for "slow" pixels.
-template <typename G> struct KcGeom { static constexpr int NBUF = G::BW * G::BH * 4 > 16384 ? 2 : 3; };
+#ifndef KC_NBUF
+#define KC_NBUF 3
+#endif
+template <typename G> struct KcGeom { static constexpr int NBUF = G::BW * G::BH * 4 > 16384 ? 2 : KC_NBUF; };
 constexpr int KC_MAXT = 256;
 
 #ifndef KC_MINB
