@@ -51,6 +51,7 @@ struct imgcorr_ctx {
     double exposure = 0.0, maxval = 65535.0;
     bool has_lens = false;
     LensConst lens{};
+    double lens_in[23] = {0};                 // K, dist, P as last given to imgcorr_set_lens (an identical call is a no-op)
     double* lens_dev = nullptr;
     float4* k2_wtab = nullptr;                // OpenCV's BilinearTab_f [32][32] (K2 tiles)
     struct GeomKey { int x0, y0, ow, oh, esz, g; };
@@ -360,6 +361,13 @@ extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], c
     if (!c) return fail(IMGCORR_ERR_INVALID, "null context");
     if (!K) { c->has_lens = false; return IMGCORR_OK; }
     if (!dist || !P) return fail(IMGCORR_ERR_INVALID, "dist / P is null");
+    {
+        // the Python mirror sets the lens on every correct() call (the reference builds a new LensDistortion per call,
+        // camera/CameraCalibration.py:565-568): the same lens again must not drop K2's geometry choice and coordinate cache
+        double in[23];
+        memcpy(in, K, 9 * sizeof(double)); memcpy(in + 9, dist, 5 * sizeof(double)); memcpy(in + 14, P, 9 * sizeof(double));
+        if (c->has_lens && c->lens_dev && memcmp(in, c->lens_in, sizeof in) == 0) return IMGCORR_OK;
+    }
     LensConst L{};
     if (!invert3x3(P, L.ir)) return fail(IMGCORR_ERR_INVALID, "new camera matrix P is singular");
     L.k1 = dist[0]; L.k2 = dist[1]; L.p1 = dist[2]; L.p2 = dist[3]; L.k3 = dist[4];
@@ -378,6 +386,7 @@ extern "C" IMGCORR_API int imgcorr_set_lens(imgcorr_ctx* c, const double K[9], c
     }
     c->lens = L;
     c->has_lens = true;
+    memcpy(c->lens_in, K, 9 * sizeof(double)); memcpy(c->lens_in + 9, dist, 5 * sizeof(double)); memcpy(c->lens_in + 14, P, 9 * sizeof(double));
     c->k2_geom.clear();
     if (!c->k2_cache.empty()) {
         DeviceGuard g(c->device);
@@ -988,7 +997,7 @@ extern "C" IMGCORR_API int imgcorr_host_fingerprint(const void* host_ptr, size_t
     if (!out || (!host_ptr && bytes)) return fail(IMGCORR_ERR_INVALID, "null pointer");
     const unsigned char* p = (const unsigned char*)host_ptr;
     unsigned nt = std::thread::hardware_concurrency();
-    if (nt > 8) nt = 8;
+    if (nt > 16) nt = 16;
     if (nt < 1 || bytes < ((size_t)4 << 20)) nt = 1;
     std::vector<unsigned long long> part(nt, 0);
     const size_t chunk = ((bytes / nt) + 31) & ~(size_t)31;

@@ -474,6 +474,11 @@ def test_k2_coordinate_cache(ip, shape, lens_kind):
                 out = e.undistort(_dev(u16)).cpu().numpy()
                 for i in range(4):
                     assert (out[i] != models.remap_model(u16[i], mapx, mapy, 0)).mean() < 1e-5
+        # the same lens set again (every correct() call of the mirror does that) keeps the cache: same bits
+        e.set_lens(K, d, P)
+        again = e.undistort(_dev(src[:1])).cpu().numpy()
+        e.set_lens(K, d, P)
+        assert np.array_equal(again, e.undistort(_dev(src[:1])).cpu().numpy()) and np.array_equal(again[0], cached[0])
         # another lens: the cached coordinates of the first must not survive
         p2 = synth.lens_moderate(H, W) if lens_kind != 'moderate' else synth.lens_strong(H, W)
         K2, d2 = synth.camera_matrix(p2), synth.dist_coeffs(p2)
