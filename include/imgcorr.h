@@ -30,7 +30,8 @@
 extern "C" {
 #endif
 
-#define IMGCORR_VERSION 100 /* 0.1.0 */
+#define IMGCORR_VERSION 200 /* 0.2.0: round 2 added imgcorr_ste_average_thr, imgcorr_stack_mean, imgcorr_scale_f64, imgcorr_subsample_f64,
+                               imgcorr_linear_fit, imgcorr_host_fingerprint, imgcorr_selftest_division and the K2 options 11, 12 */
 
 #if defined(__GNUC__)
 #define IMGCORR_API __attribute__((visibility("default")))

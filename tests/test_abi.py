@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
         assert name in _lib.SIGNATURES, 'ctypes signature missing for %s' % name
     assert set(_lib.SIGNATURES) == set(_declared())
-    assert handle.imgcorr_version() == 100
+    assert handle.imgcorr_version() == 200
 
 
 def test_no_device_means_loud_failure_not_fallback():
