@@ -647,7 +647,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--frames', type=int, default=256, help='frames per GPU per step')
     ap.add_argument('--group', type=int, default=32, help='frames per K1/K2 launch inside the chain')
-    ap.add_argument('--overlap', type=int, default=0, help='1: K1 of the next group overlaps K2 of the current one')
+    ap.add_argument('--overlap', type=int, default=1, help='1 (library default): K1 of the next group overlaps K2 of the current one')
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--e2e-pool', type=int, default=32, help='pinned host frames cycled by the end-to-end leg')
     ap.add_argument('--e2e-steps', type=int, default=3)

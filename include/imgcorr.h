@@ -75,7 +75,7 @@ enum {
     IMGCORR_OPT_RAW_FRAME_GAP = 8,  /* bytes between the end of one raw frame and the start of the next: reader/elbin.py:23-32
                                        (a 20-byte header precedes every frame).  Not available for the *_host entry point. */
     IMGCORR_OPT_CHAIN_OVERLAP = 10, /* imgcorr_correct_batch: run K1 of the next frame group on an internal high-priority stream while K2
-                                       of the current group runs on the caller's stream (default 0 = everything on the caller's stream) */
+                                       of the current group runs on the caller's stream (default 1; 0 = everything on the caller's stream) */
     IMGCORR_OPT_K2_COORD_CACHE = 11, /* 1 (default): the first tiled K2 launch for a lens / output window stores the packed fixed-point source
                                        coordinates it computed (4 bytes per pixel of device memory, at most two windows), later launches read them
                                        instead of re-evaluating the float64 lens model; 0: evaluate on every launch */

@@ -828,6 +828,7 @@ def test_chain_overlap_mode_is_identical(ip):
     frames = _dev(np.stack([synth.scene(H, W, 50 + i, np.uint16) for i in range(n)]))
     e = ip.engine_mod.get_engine(H, W)
     _quiet(cal.correct, frames[0].cpu().numpy(), threshold=0.1)            # uploads the calibration into the engine
+    e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 0)                          # reference result: everything on one stream
     want = e.correct_batch(frames, threshold=0.1).cpu().numpy()
     try:
         e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 1)
@@ -841,7 +842,7 @@ def test_chain_overlap_mode_is_identical(ip):
                 e.profile_read()
     finally:
         e.set_option(ip.lib_mod.OPT_PROFILE, 0)
-        e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 0)
+        e.set_option(ip.lib_mod.OPT_CHAIN_OVERLAP, 1)                      # the library default
         e.set_option(ip.lib_mod.OPT_CHAIN_GROUP, 16)
 
 
