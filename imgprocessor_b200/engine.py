@@ -534,7 +534,8 @@ MAX_CACHED_ENGINES = 16
 
 def get_engine(height, width, device=None):
     """the cached engine (context: calibration copies, scratch, pinned rings) for a device and frame shape.  At most
-    MAX_CACHED_ENGINES are kept; the least recently used one is closed (its device memory freed) when a new shape arrives."""
+    MAX_CACHED_ENGINES are kept; the least recently used one is dropped from the cache when a new shape arrives — its
+    context (device memory) is freed as soon as nobody else holds the engine (Engine.__del__), never under a caller's feet."""
     tt = require_cuda()
     idx = tt.cuda.current_device() if device is None else tt.device('cuda', device).index
     key = (idx, int(height), int(width))
@@ -542,7 +543,6 @@ def get_engine(height, width, device=None):
     if e is None or e._h is None:
         e = Engine(height, width, idx)
         while len(_ENGINES) >= MAX_CACHED_ENGINES:
-            old = _ENGINES.pop(next(iter(_ENGINES)))
-            old.close()
+            _ENGINES.pop(next(iter(_ENGINES)))
     _ENGINES[key] = e
     return e
